@@ -1,0 +1,211 @@
+/* noahmp_b200.h — C-ABI of the B200-native Noah-MP column-physics step.
+ *
+ * This is the drop-in boundary for the reference's
+ *     SUBROUTINE noahmplsm(...)            phys/module_sf_noahmpdrv.F90:11-44 (decls :51-211)
+ * as called once per model step by
+ *     land_driver_exe                      driver/module_hrldas_noahmp_driver.F90:386-415
+ * plus the table loaders it depends on
+ *     read_mp_veg_parameters(DATASET)      phys/module_sf_noahmplsm.F90:274-404   (MPTABLE.TBL)
+ *     SOIL_VEG_GEN_PARM(MMINLU,MMINSL)     phys/module_sf_noahmpdrv.F90:1528-1821 (VEGPARM/SOILPARM/GENPARM.TBL)
+ *
+ * Plain C: pointers, ints, floats. No torch / CUDA types cross this boundary.  Host arrays use
+ * the Fortran memory layout of the reference (2-D A(i,j): i fastest; 3-D A(i,k,j): i fastest,
+ * layer k in the middle), REAL = float, INTEGER = int32.  INTEGRATION.md shows the
+ * ISO_C_BINDING shim that forwards the unchanged Fortran `noahmplsm` signature here.
+ */
+#ifndef NOAHMP_B200_H
+#define NOAHMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOAHMP_MVT 27      /* NOAHMP_VEG_PARAMETERS::MVT, noahmplsm.F90:206 */
+#define NOAHMP_MBAND 2     /* noahmplsm.F90:207 */
+#define NOAHMP_NLUS 50     /* noahmp_globals::NLUS, noahmplsm.F90:42 */
+#define NOAHMP_NSLTYPE 30  /* noahmplsm.F90:83 */
+#define NOAHMP_NSLOPE 30   /* noahmplsm.F90:100 */
+#define NOAHMP_NSOIL 4     /* the path is built for NSOIL=4 (glacier PHASECHANGE hard-codes it, glacier.F90:1804-1908) */
+#define NOAHMP_NSNOW 3     /* noahmpdrv.F90:367 */
+
+/* Parameter tables, exactly the module data the reference physics reads.
+ * 2-D Fortran arrays X(MVT,n) are stored x[n][MVT] (same memory order). Index 0 = Fortran index 1. */
+typedef struct noahmp_tables {
+  /* ---- MPTABLE.TBL (noahmplsm.F90:209-259, namelist :291-301) ---- */
+  int32_t nveg;
+  int32_t isurban_mp; /* PRIVATE in the reference; kept for completeness, unused by physics */
+  int32_t iswater, isbarren, issnow, eblforest;
+  float ch2op[NOAHMP_MVT], dleaf[NOAHMP_MVT], z0mvt[NOAHMP_MVT], hvt[NOAHMP_MVT], hvb[NOAHMP_MVT];
+  float den[NOAHMP_MVT], rc[NOAHMP_MVT];
+  float rhol[NOAHMP_MBAND][NOAHMP_MVT], rhos[NOAHMP_MBAND][NOAHMP_MVT];
+  float taul[NOAHMP_MBAND][NOAHMP_MVT], taus[NOAHMP_MBAND][NOAHMP_MVT];
+  float xl[NOAHMP_MVT], cwpvt[NOAHMP_MVT], c3psn[NOAHMP_MVT], kc25[NOAHMP_MVT], akc[NOAHMP_MVT];
+  float ko25[NOAHMP_MVT], ako[NOAHMP_MVT], avcmx[NOAHMP_MVT], aqe[NOAHMP_MVT], ltovrc[NOAHMP_MVT];
+  float dilefc[NOAHMP_MVT], dilefw[NOAHMP_MVT], rmf25[NOAHMP_MVT], sla[NOAHMP_MVT], fragr[NOAHMP_MVT];
+  float tmin[NOAHMP_MVT], vcmx25[NOAHMP_MVT], tdlef[NOAHMP_MVT], bp[NOAHMP_MVT], mp[NOAHMP_MVT];
+  float qe25[NOAHMP_MVT], rms25[NOAHMP_MVT], rmr25[NOAHMP_MVT], arm[NOAHMP_MVT], folnmx[NOAHMP_MVT];
+  float wdpool[NOAHMP_MVT], wrrat[NOAHMP_MVT], mrp[NOAHMP_MVT];
+  float saim[12][NOAHMP_MVT], laim[12][NOAHMP_MVT];
+  float slarea[NOAHMP_MVT], eps[5][NOAHMP_MVT];
+  /* ---- VEGPARM.TBL (noahmpdrv.F90:1569-1646); only NROTBL,RSTBL,RGLTBL,HSTBL,TOPT,RSMAX reach physics ---- */
+  int32_t lucats;
+  int32_t nrotbl[NOAHMP_NLUS];
+  float shdtbl[NOAHMP_NLUS], rstbl[NOAHMP_NLUS], rgltbl[NOAHMP_NLUS], hstbl[NOAHMP_NLUS];
+  float snuptbl[NOAHMP_NLUS], maxalb[NOAHMP_NLUS], laimintbl[NOAHMP_NLUS], laimaxtbl[NOAHMP_NLUS];
+  float emissmintbl[NOAHMP_NLUS], emissmaxtbl[NOAHMP_NLUS], albedomintbl[NOAHMP_NLUS], albedomaxtbl[NOAHMP_NLUS];
+  float z0mintbl[NOAHMP_NLUS], z0maxtbl[NOAHMP_NLUS], ztopvtbl[NOAHMP_NLUS], zbotvtbl[NOAHMP_NLUS];
+  float topt_data, cmcmax_data, cfactr_data, rsmax_data;
+  int32_t bare, natural;
+  /* ---- SOILPARM.TBL (noahmpdrv.F90:1681-1726) ---- */
+  int32_t slcats;
+  float bb[NOAHMP_NSLTYPE], drysmc[NOAHMP_NSLTYPE], f11[NOAHMP_NSLTYPE], maxsmc[NOAHMP_NSLTYPE];
+  float refsmc[NOAHMP_NSLTYPE], satpsi[NOAHMP_NSLTYPE], satdk[NOAHMP_NSLTYPE], satdw[NOAHMP_NSLTYPE];
+  float wltsmc[NOAHMP_NSLTYPE], qtz[NOAHMP_NSLTYPE];
+  /* ---- GENPARM.TBL (noahmpdrv.F90:1755-1800) ---- */
+  int32_t slpcats;
+  float slope_data[NOAHMP_NSLOPE];
+  float sbeta_data, fxexp_data, csoil_data, salp_data, refdk_data, refkdt_data, frzk_data, zbot_data;
+  float czil_data, smlow_data, smhigh_data, lvcoef_data;
+} noahmp_tables;
+
+/* Argument list of `noahmplsm` (noahmpdrv.F90:11-44) as a struct of the same names, same order.
+ * Arrays are the caller's (host) arrays in Fortran layout with memory bounds ims:ime, kms:kme,
+ * jms:jme (soil arrays 1:nsoil, snow arrays -2:0, ZSNSOXY -2:nsoil in the middle dimension). */
+typedef struct noahmp_lsm_args {
+  /* IN: time/space */
+  int32_t itimestep, yr;
+  float julian;
+  const float* coszin;
+  const float* xlatin;
+  const float* dz8w; /* (ims:ime,kms:kme,jms:jme) */
+  float dt;
+  const float* dzs; /* (1:nsoil) */
+  int32_t nsoil;
+  float dx;
+  const int32_t* ivgtyp;
+  const int32_t* isltyp;
+  const float* vegfra;
+  const float* vegmax;
+  const float* tmn;
+  const float* xland;
+  const float* xice;
+  float xice_thres;
+  int32_t isice, isurban;
+  /* IN: options */
+  int32_t idveg, iopt_crs, iopt_btr, iopt_run, iopt_sfc, iopt_frz, iopt_inf, iopt_rad, iopt_alb;
+  int32_t iopt_snf, iopt_tbot, iopt_stc, iz0tlnd;
+  /* IN: forcing */
+  const float *t3d, *qv3d, *u_phy, *v_phy; /* 3-D (ims:ime,kms:kme,jms:jme) */
+  const float *swdown, *glw;
+  const float* p8w3d; /* 3-D */
+  const float* rainbl;
+  /* INOUT: generic LSM (21) */
+  float *tsk, *hfx, *qfx, *lh, *grdflx, *smstav, *smstot, *sfcrunoff, *udrunoff, *albedo, *snowc;
+  float *smois, *sh2o, *tslb; /* (ims:ime,1:nsoil,jms:jme) */
+  float *snow, *snowh, *canwat, *acsnom, *acsnow, *emiss, *qsfc;
+  /* INOUT: Noah-MP (34) */
+  int32_t* isnowxy;
+  float *tvxy, *tgxy, *canicexy, *canliqxy, *eahxy, *tahxy, *cmxy, *chxy, *fwetxy, *sneqvoxy, *alboldxy;
+  float *qsnowxy, *wslakexy, *zwtxy, *waxy, *wtxy;
+  float* tsnoxy;  /* (ims:ime,-2:0,jms:jme) */
+  float* zsnsoxy; /* (ims:ime,-2:nsoil,jms:jme) */
+  float *snicexy, *snliqxy; /* (ims:ime,-2:0,jms:jme) */
+  float *lfmassxy, *rtmassxy, *stmassxy, *woodxy, *stblcpxy, *fastcpxy, *xlaixy, *xsaixy, *taussxy;
+  float* smoiseq; /* (ims:ime,1:nsoil,jms:jme) */
+  float *smcwtdxy, *deeprechxy, *rechxy;
+  /* OUT: Noah-MP (44) */
+  float *t2mvxy, *t2mbxy, *q2mvxy, *q2mbxy, *tradxy, *neexy, *gppxy, *nppxy, *fvegxy, *runsfxy;
+  float *runsbxy, *ecanxy, *edirxy, *etranxy, *fsaxy, *firaxy, *aparxy, *psnxy, *savxy, *sagxy;
+  float *rssunxy, *rsshaxy, *bgapxy, *wgapxy, *tgvxy, *tgbxy, *chvxy, *chbxy, *shgxy, *shcxy;
+  float *shbxy, *evgxy, *evbxy, *ghvxy, *ghbxy, *irgxy, *ircxy, *irbxy, *trxy, *evcxy;
+  float *chleafxy, *chucxy, *chv2xy, *chb2xy;
+  /* index bounds */
+  int32_t ids, ide, jds, jde, kds, kde;
+  int32_t ims, ime, jms, jme, kms, kme;
+  int32_t its, ite, jts, jte, kts, kte;
+} noahmp_lsm_args;
+
+/* Error record: the reference aborts the process via wrf_error_fatal (util/module_wrf_utilities.F:12-24)
+ * from ERROR (noahmplsm.F90:1164-1226), ERROR_GLACIER (glacier.F90:2932-2970), ENERGY (:1787) etc.
+ * Here the step returns a status and the first failing column; the Fortran shim turns a nonzero
+ * status into the reference's wrf_error_fatal message. */
+enum {
+  NOAHMP_OK = 0,
+  NOAHMP_ERR_ERRSW = 1,    /* "Stop in Noah-MP" (noahmplsm.F90:1185)                      */
+  NOAHMP_ERR_ERRENG = 2,   /* "Energy budget problem in NOAHMP LSM" (noahmplsm.F90:1196) */
+  NOAHMP_ERR_ERRWAT = 3,   /* "Water budget problem in NOAHMP LSM" (noahmplsm.F90:1221)  */
+  NOAHMP_ERR_FIRE = 4,     /* "STOP in Noah-MP" emitted longwave <0 (noahmplsm.F90:1792)  */
+  NOAHMP_ERR_HCAN = 5,     /* "CRITICAL PROBLEM: HCAN <= ZPD" (noahmplsm.F90:3289)        */
+  NOAHMP_ERR_ZLVL = 6,     /* "STOP in Noah-MP" ZLVL <= ZPD (noahmplsm.F90:4124)          */
+  NOAHMP_ERR_REDPRM = 7,   /* REDPRM range checks (noahmplsm.F90:9266-9277, :9340)        */
+  NOAHMP_ERR_OPTION = 8,   /* unsupported option value (opt_sfc 3/4: non-functional offline) */
+  NOAHMP_ERR_CUDA = 100,   /* CUDA runtime failure; see noahmp_b200_last_error()          */
+  NOAHMP_ERR_ARG = 101
+};
+
+typedef struct noahmp_status {
+  int32_t code;      /* one of the enum above */
+  int32_t i, j;      /* Fortran (i,j) of the first failing column, 0 if none */
+  int32_t count;     /* number of failing columns in this step */
+  float value;       /* offending residual (ERRSW / ERRENG / ERRWAT ...) */
+} noahmp_status;
+
+typedef struct noahmp_b200_ctx noahmp_b200_ctx; /* opaque */
+
+/* ---- table loading: replaces read_mp_veg_parameters + SOIL_VEG_GEN_PARM ------------------- */
+/* Reads MPTABLE.TBL, VEGPARM.TBL, SOILPARM.TBL, GENPARM.TBL from `dir` (the reference reads the
+ * CWD; pass "." for identical behaviour). dataset = "USGS" | "MODIFIED_IGBP_MODIS_NOAH",
+ * soil = "STAS". Returns 0 on success. Host-only, no GPU needed. */
+int noahmp_b200_read_tables(const char* dir, const char* dataset, const char* soil, noahmp_tables* out);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Creates a device context on CUDA device `device` for a tile of ni x nj columns. Fails (returns
+ * NULL) when no CUDA device is usable: there is no CPU fallback. */
+noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int ni, int nj);
+void noahmp_b200_destroy(noahmp_b200_ctx* ctx);
+const char* noahmp_b200_last_error(void);
+
+/* mode flags for noahmp_b200_set_mode */
+#define NOAHMP_SYNC_FULL 0     /* every call uploads INOUT state and downloads INOUT+OUT: strict drop-in */
+#define NOAHMP_SYNC_RESIDENT 1 /* state stays in HBM; forcing is uploaded each call; host INOUT/OUT arrays
+                                  are refreshed only by noahmp_b200_sync_host (output/restart cadence) */
+int noahmp_b200_set_mode(noahmp_b200_ctx* ctx, int sync_mode);
+
+/* ---- the step: replaces `CALL noahmplsm(...)` ------------------------------------------------ */
+int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, noahmp_status* status);
+
+/* Refresh the caller's INOUT/OUT host arrays from HBM (RESIDENT mode). */
+int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
+
+/* ---- device-resident stepping used by bench.py / drivers that keep forcing on the GPU -------- */
+/* Upload static fields + initial state from host arrays (Fortran layout) once. */
+int noahmp_b200_upload(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
+/* Pointers to device forcing staging buffers (column-compact order is internal; these are in the
+ * Fortran 2-D (i,j) layout, ni*nj floats each) so a driver can fill them on the device. Order:
+ * 0 COSZIN 1 T3D(k=1) 2 QV3D(k=1) 3 U_PHY 4 V_PHY 5 SWDOWN 6 GLW 7 P8W3D(k=1) 8 P8W3D(k=2) 9 RAINBL
+ * 10 VEGFRA 11 DZ8W(k=1) */
+#define NOAHMP_NFORCING 12
+int noahmp_b200_device_forcing(noahmp_b200_ctx* ctx, float** dev_ptrs /* [NOAHMP_NFORCING] */);
+/* One step entirely on the device with the forcing currently in the staging buffers.
+ * scalars as in noahmplsm; `stream` is a cudaStream_t passed as void* (NULL = the context's stream). */
+int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt,
+                            void* stream);
+/* Fetch status of the last step (synchronises the context stream). */
+int noahmp_b200_get_status(noahmp_b200_ctx* ctx, noahmp_status* status);
+/* Number of kernels launched by this context since creation (for bench accounting). */
+long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx);
+/* Column census: [0] land columns, [1] glacier columns, [2] sea-ice columns, [3] water columns. */
+int noahmp_b200_census(const noahmp_b200_ctx* ctx, int64_t counts[4]);
+
+/* ---- domain decomposition: replaces mpp_land_partition arithmetic ----------------------------
+ * mpp/module_mpp_land.F90:124-141 (process grid), :245-288 (tile extents). All 1-based inclusive. */
+void noahmp_b200_proc_grid(int nproc, int* nprocx, int* nprocy);
+void noahmp_b200_tile(int global_nx, int global_ny, int nproc, int rank, int* xstart, int* xend,
+                      int* ystart, int* yend);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOAHMP_B200_H */

@@ -1,0 +1,67 @@
+"""ctypes loader for the CPU ORACLE (oracle/libnmo_oracle.so) — test infrastructure.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module. The product path (noahmp_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from noahmp_b200 import _capi  # noqa: E402
+
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libnmo_oracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.nmo_noahmplsm.argtypes = [C.POINTER(_capi.NoahmpLsmArgs), C.POINTER(_capi.NoahmpTables),
+                                       C.POINTER(_capi.NoahmpStatus), C.c_int, C.POINTER(C.c_int32)]
+        _LIB.nmo_noahmplsm.restype = C.c_int
+        _LIB.nmo_math1.argtypes = [C.c_int, C.c_float, C.c_float]
+        _LIB.nmo_math1.restype = C.c_float
+        _LIB.nmo_math_array.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        _LIB.nmo_esat.argtypes = [C.c_float, C.POINTER(C.c_float)]
+    return _LIB
+
+
+def set_math_mode(mode):
+    """0 = host libm (reference-like), 1 = portable nmp_math.h (bit-comparable with the GPU parity build)."""
+    lib().nmo_set_math_mode(int(mode))
+
+
+def noahmplsm(arrays, scalars, tables_struct, nthreads=1, want_iters=False):
+    """One call of the oracle's noahmplsm on host arrays (updated in place). Returns (status, iters)."""
+    a = _capi.make_args(arrays, scalars)
+    st = _capi.NoahmpStatus()
+    it = None
+    itp = None
+    if want_iters:
+        it = np.zeros(arrays["tsk"].shape, np.int32)
+        itp = it.ctypes.data_as(C.POINTER(C.c_int32))
+    lib().nmo_noahmplsm(C.byref(a), C.byref(tables_struct), C.byref(st), int(nthreads), itp)
+    return st, it
+
+
+def math_array(fn, x, y=None):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    yp = None
+    if y is not None:
+        y = np.ascontiguousarray(y, np.float32)
+        yp = y.ctypes.data
+    lib().nmo_math_array(fn, x.ctypes.data, yp, out.ctypes.data, x.size)
+    return out
