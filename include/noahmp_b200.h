@@ -159,6 +159,11 @@ typedef struct noahmp_b200_ctx noahmp_b200_ctx; /* opaque */
  * CWD; pass "." for identical behaviour). dataset = "USGS" | "MODIFIED_IGBP_MODIS_NOAH",
  * soil = "STAS". Returns 0 on success. Host-only, no GPU needed. */
 int noahmp_b200_read_tables(const char* dir, const char* dataset, const char* soil, noahmp_tables* out);
+/* Message of the last table-reading failure (the text the reference would pass to wrf_error_fatal). */
+const char* noahmp_b200_tables_error(void);
+/* sizeof(noahmp_tables) / sizeof(noahmp_lsm_args) as compiled into the library (ABI checks of bindings). */
+unsigned long long noahmp_b200_sizeof_tables(void);
+unsigned long long noahmp_b200_sizeof_args(void);
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* Creates a device context on CUDA device `device` for a tile of ni x nj columns. Fails (returns
@@ -173,11 +178,25 @@ const char* noahmp_b200_last_error(void);
                                   are refreshed only by noahmp_b200_sync_host (output/restart cadence) */
 int noahmp_b200_set_mode(noahmp_b200_ctx* ctx, int sync_mode);
 
+/* Arithmetic of the physics kernels.  FAST: CUDA libdevice single-precision functions with FMA contraction
+ * (the production build).  PARITY: every transcendental through csrc/nmp_math.h and no FMA contraction, which
+ * makes the results bit-identical with the CPU oracle's portable-math mode (used by the parity tests; also
+ * selectable with the environment variable NOAHMP_B200_MATH=parity). */
+#define NOAHMP_MATH_FAST 0
+#define NOAHMP_MATH_PARITY 1
+int noahmp_b200_set_math(noahmp_b200_ctx* ctx, int math_mode);
+/* Name of the kernel instantiation the last step used: "default" / "dynveg" (opt_* compiled in as template
+ * constants) or "runtime" (options read at run time). */
+const char* noahmp_b200_kernel_variant(const noahmp_b200_ctx* ctx);
+
 /* ---- the step: replaces `CALL noahmplsm(...)` ------------------------------------------------ */
 int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, noahmp_status* status);
 
 /* Refresh the caller's INOUT/OUT host arrays from HBM (RESIDENT mode). */
 int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
+
+/* Refresh ONE caller array (named like the noahmp_lsm_args member, e.g. "tsk") from HBM in RESIDENT mode. */
+int noahmp_b200_fetch(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, const char* field);
 
 /* ---- device-resident stepping used by bench.py / drivers that keep forcing on the GPU -------- */
 /* Upload static fields + initial state from host arrays (Fortran layout) once. */
@@ -188,6 +207,9 @@ int noahmp_b200_upload(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
  * 10 VEGFRA 11 DZ8W(k=1) */
 #define NOAHMP_NFORCING 12
 int noahmp_b200_device_forcing(noahmp_b200_ctx* ctx, float** dev_ptrs /* [NOAHMP_NFORCING] */);
+/* Use caller-owned device planes (same order/layout) as the forcing of the following steps; NULL = back to
+ * the context's own staging planes. */
+int noahmp_b200_bind_forcing(noahmp_b200_ctx* ctx, float* const* dev_ptrs /* [NOAHMP_NFORCING] or NULL */);
 /* One step entirely on the device with the forcing currently in the staging buffers.
  * scalars as in noahmplsm; `stream` is a cudaStream_t passed as void* (NULL = the context's stream). */
 int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt,
@@ -198,6 +220,16 @@ int noahmp_b200_get_status(noahmp_b200_ctx* ctx, noahmp_status* status);
 long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx);
 /* Column census: [0] land columns, [1] glacier columns, [2] sea-ice columns, [3] water columns. */
 int noahmp_b200_census(const noahmp_b200_ctx* ctx, int64_t counts[4]);
+
+/* Compact column -> 0-based tile-local cell index ((i-1) + (j-1)*ni), ordered land | glacier | sea-ice, each
+ * class in grid order: the permutation the kernels run on (bit-exact contract, tests/test_partition.py). */
+int noahmp_b200_column_map(noahmp_b200_ctx* ctx, int32_t* cells, long long capacity);
+/* Device pointer to layer `layer` (0-based) of a state field (named like the noahmp_lsm_args member) in the
+ * column-compact structure of arrays; *np = number of active columns (the plane length). */
+float* noahmp_b200_device_state(noahmp_b200_ctx* ctx, const char* field, int layer, long long* np);
+/* Optional diagnostic: per-cell VEGE_FLUX pass count of the last step (ni*nj int32, grid order). */
+int noahmp_b200_enable_iteration_counts(noahmp_b200_ctx* ctx, int enable);
+int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out);
 
 /* ---- domain decomposition: replaces mpp_land_partition arithmetic ----------------------------
  * mpp/module_mpp_land.F90:124-141 (process grid), :245-288 (tile extents). All 1-based inclusive. */

@@ -1,0 +1,387 @@
+// nmp_kernels.cuh — the column-physics kernels: the ILOOP body of `noahmplsm`
+// (phys/module_sf_noahmpdrv.F90:424-837) for land and glacier columns.
+//
+// Included by nmp_kernels_fast.cu (NMP_PARITY=0: libdevice math, FMA contraction) and by
+// nmp_kernels_parity.cu (NMP_PARITY=1, compiled with -fmad=false: bit-identical to the CPU oracle's
+// portable-math mode).  One thread = one column; columns of one class are contiguous in the compact
+// state, so the land and the glacier kernels never diverge on column class.
+#pragma once
+#include <cstdlib>
+#include "nmp_fields.h"
+#include "nmp_glacier.cuh"
+
+namespace {
+
+using namespace nmp;
+using nmpf::StepParams;
+
+struct ColumnIO {
+  const StepParams& p;
+  long long n;  // compact column
+  int cell;
+  __device__ ColumnIO(const StepParams& p_, long long n_) : p(p_), n(n_), cell(p_.cell[n_]) {}
+  __device__ float forc(int f) const { return __ldg(p.forc[f] + cell); }
+  __device__ float stat(int f) const { return __ldg(p.stat[f] + cell); }
+  __device__ int stati(int f) const { return __float_as_int(__ldg(p.stat[f] + cell)); }
+  __device__ float ld(int slot) const { return p.state[(long long)slot * p.np + n]; }
+  __device__ int ldi(int slot) const { return __float_as_int(p.state[(long long)slot * p.np + n]); }
+  __device__ void st(int slot, float v) const { p.state[(long long)slot * p.np + n] = v; }
+  __device__ void sti(int slot, int v) const { p.state[(long long)slot * p.np + n] = __int_as_float(v); }
+};
+
+__device__ __forceinline__ void report_error(const StepParams& p, int cell, int code, float value) {
+  atomicAdd(p.err_count, 1);
+  unsigned long long key = ((unsigned long long)(unsigned)cell << 39) | ((unsigned long long)(code & 0x7f) << 32) |
+                           (unsigned long long)__float_as_uint(value);
+  atomicMin(p.err_key, key);
+}
+
+// gather of the pieces shared by land and glacier columns (noahmpdrv.F90:449-520)
+__device__ __forceinline__ void load_common(const ColumnIO& io, const StepParams& p, Col& s) {
+  s.COSZ = io.forc(nmpf::FC_COSZIN);
+  s.LAT = io.stat(nmpf::ST_XLATIN);
+  s.ZLVL = 0.5f * io.forc(nmpf::FC_DZ8W);
+  s.TBOT = io.stat(nmpf::ST_TMN);
+  s.SFCTMP = io.forc(nmpf::FC_T);
+  const float qv = io.forc(nmpf::FC_QV);
+  s.Q2 = qv / (1.0f + qv);
+  s.UU = io.forc(nmpf::FC_U);
+  s.VV = io.forc(nmpf::FC_V);
+  s.SOLDN = io.forc(nmpf::FC_SWDOWN);
+  s.LWDN = io.forc(nmpf::FC_GLW);
+  const float p1 = io.forc(nmpf::FC_P1);
+  s.SFCPRS = (io.forc(nmpf::FC_P2) + p1) * 0.5f;
+  s.PSFC = p1;
+  s.PRCP = io.forc(nmpf::FC_RAINBL) / p.dt;
+  s.DT = p.dt;
+  s.JULIAN = p.julian;
+  s.YEARLEN = p.yearlen;
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) s.ZSOIL(K) = p.zsoil[K - 1];
+
+  s.ISNOW = io.ldi(NMP_SLOT(isnowxy));
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) {
+    s.SMC(K) = io.ld(NMP_SLOT(smois) + K - 1);
+    s.SH2O(K) = io.ld(NMP_SLOT(sh2o) + K - 1);
+    s.STC(K) = io.ld(NMP_SLOT(tslb) + K - 1);
+  }
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) {
+    s.STC(K) = io.ld(NMP_SLOT(tsnoxy) + K + 2);
+    s.SNICE(K) = io.ld(NMP_SLOT(snicexy) + K + 2);
+    s.SNLIQ(K) = io.ld(NMP_SLOT(snliqxy) + K + 2);
+  }
+#pragma unroll
+  for (int K = -2; K <= NSOIL; ++K) s.ZSNSO(K) = io.ld(NMP_SLOT(zsnsoxy) + K + 2);
+  s.SNEQV = io.ld(NMP_SLOT(snow));
+  s.SNOWH = io.ld(NMP_SLOT(snowh));
+  s.QSFC = io.ld(NMP_SLOT(qsfc));
+  s.TG = io.ld(NMP_SLOT(tgxy));
+  s.CM = io.ld(NMP_SLOT(cmxy));
+  s.CH = io.ld(NMP_SLOT(chxy));
+  s.SNEQVO = io.ld(NMP_SLOT(sneqvoxy));
+  s.ALBOLD = io.ld(NMP_SLOT(alboldxy));
+  s.QSNOW = io.ld(NMP_SLOT(qsnowxy));
+  s.TAUSS = io.ld(NMP_SLOT(taussxy));
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) {
+    s.FICEOLD(K) = 0.0f;
+    if (K > s.ISNOW) s.FICEOLD(K) = s.SNICE(K) / (s.SNICE(K) + s.SNLIQ(K));
+  }
+}
+
+// scatter of one column (noahmpdrv.F90:728-835); quantities are already set for the column class
+struct ColumnOut {
+  float QFX, LH, TV, CANICE, CANLIQ, EAH, TAH, FWET, WSLAKE, ZWT, WA, WT, LFMASS, RTMASS, STMASS, WOOD, STBLCP,
+      FASTCP, PLAI, PSAI, T2MV, T2MB, Q2MV, Q2MB, NEE, GPP, NPP, FVEGMP, ECAN, ETRAN, ESOIL, APAR, PSN, SAV, RSSUN,
+      RSSHA, BGAP, WGAP, TGV, TGB, CHV, CHB, IRC, IRG, SHC, SHG, EVG, GHV, IRB, SHB, EVB, GHB, TR, EVC, CHLEAF, CHUC,
+      CHV2, CHB2, FSNO, RECH, DEEPRECH, SMCWTD;
+};
+
+__device__ __forceinline__ void store_column(const ColumnIO& io, const StepParams& p, const Col& s,
+                                             const ColumnOut& o) {
+  io.st(NMP_SLOT(tsk), s.TRAD);
+  io.st(NMP_SLOT(hfx), s.FSH);
+  io.st(NMP_SLOT(qfx), o.QFX);
+  io.st(NMP_SLOT(lh), o.LH);
+  io.st(NMP_SLOT(grdflx), s.SSOIL);
+  io.st(NMP_SLOT(smstav), 0.0f);
+  io.st(NMP_SLOT(smstot), 0.0f);
+  io.st(NMP_SLOT(sfcrunoff), io.ld(NMP_SLOT(sfcrunoff)) + s.RUNSRF * p.dt);
+  io.st(NMP_SLOT(udrunoff), io.ld(NMP_SLOT(udrunoff)) + s.RUNSUB * p.dt);
+  if (s.ALBEDO > -999.f) io.st(NMP_SLOT(albedo), s.ALBEDO);
+  io.st(NMP_SLOT(snowc), o.FSNO);
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) {
+    io.st(NMP_SLOT(smois) + K - 1, s.SMC(K));
+    io.st(NMP_SLOT(sh2o) + K - 1, s.SH2O(K));
+    io.st(NMP_SLOT(tslb) + K - 1, s.STC(K));
+  }
+  io.st(NMP_SLOT(snow), s.SNEQV);
+  io.st(NMP_SLOT(snowh), s.SNOWH);
+  io.st(NMP_SLOT(canwat), o.CANLIQ + o.CANICE);
+  io.st(NMP_SLOT(acsnow), io.ld(NMP_SLOT(acsnow)) + s.PRCP * s.FPICE);
+  io.st(NMP_SLOT(acsnom), io.ld(NMP_SLOT(acsnom)) + s.QSNBOT * p.dt + s.PONDING + s.PONDING1 + s.PONDING2);
+  io.st(NMP_SLOT(emiss), s.EMISSI);
+  io.st(NMP_SLOT(qsfc), s.QSFC);
+  io.sti(NMP_SLOT(isnowxy), s.ISNOW);
+  io.st(NMP_SLOT(tvxy), o.TV);
+  io.st(NMP_SLOT(tgxy), s.TG);
+  io.st(NMP_SLOT(canliqxy), o.CANLIQ);
+  io.st(NMP_SLOT(canicexy), o.CANICE);
+  io.st(NMP_SLOT(eahxy), o.EAH);
+  io.st(NMP_SLOT(tahxy), o.TAH);
+  io.st(NMP_SLOT(cmxy), s.CM);
+  io.st(NMP_SLOT(chxy), s.CH);
+  io.st(NMP_SLOT(fwetxy), o.FWET);
+  io.st(NMP_SLOT(sneqvoxy), s.SNEQVO);
+  io.st(NMP_SLOT(alboldxy), s.ALBOLD);
+  io.st(NMP_SLOT(qsnowxy), s.QSNOW);
+  io.st(NMP_SLOT(wslakexy), o.WSLAKE);
+  io.st(NMP_SLOT(zwtxy), o.ZWT);
+  io.st(NMP_SLOT(waxy), o.WA);
+  io.st(NMP_SLOT(wtxy), o.WT);
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) {
+    io.st(NMP_SLOT(tsnoxy) + K + 2, s.STC(K));
+    io.st(NMP_SLOT(snicexy) + K + 2, s.SNICE(K));
+    io.st(NMP_SLOT(snliqxy) + K + 2, s.SNLIQ(K));
+  }
+#pragma unroll
+  for (int K = -2; K <= NSOIL; ++K) io.st(NMP_SLOT(zsnsoxy) + K + 2, s.ZSNSO(K));
+  io.st(NMP_SLOT(lfmassxy), o.LFMASS);
+  io.st(NMP_SLOT(rtmassxy), o.RTMASS);
+  io.st(NMP_SLOT(stmassxy), o.STMASS);
+  io.st(NMP_SLOT(woodxy), o.WOOD);
+  io.st(NMP_SLOT(stblcpxy), o.STBLCP);
+  io.st(NMP_SLOT(fastcpxy), o.FASTCP);
+  io.st(NMP_SLOT(xlaixy), o.PLAI);
+  io.st(NMP_SLOT(xsaixy), o.PSAI);
+  io.st(NMP_SLOT(taussxy), s.TAUSS);
+  io.st(NMP_SLOT(t2mvxy), o.T2MV);
+  io.st(NMP_SLOT(t2mbxy), o.T2MB);
+  io.st(NMP_SLOT(q2mvxy), o.Q2MV / (1.0f - o.Q2MV));
+  io.st(NMP_SLOT(q2mbxy), o.Q2MB / (1.0f - o.Q2MB));
+  io.st(NMP_SLOT(tradxy), s.TRAD);
+  io.st(NMP_SLOT(neexy), o.NEE);
+  io.st(NMP_SLOT(gppxy), o.GPP);
+  io.st(NMP_SLOT(nppxy), o.NPP);
+  io.st(NMP_SLOT(fvegxy), o.FVEGMP);
+  io.st(NMP_SLOT(runsfxy), s.RUNSRF);
+  io.st(NMP_SLOT(runsbxy), s.RUNSUB);
+  io.st(NMP_SLOT(ecanxy), o.ECAN);
+  io.st(NMP_SLOT(edirxy), o.ESOIL);
+  io.st(NMP_SLOT(etranxy), o.ETRAN);
+  io.st(NMP_SLOT(fsaxy), s.FSA);
+  io.st(NMP_SLOT(firaxy), s.FIRA);
+  io.st(NMP_SLOT(aparxy), o.APAR);
+  io.st(NMP_SLOT(psnxy), o.PSN);
+  io.st(NMP_SLOT(savxy), o.SAV);
+  io.st(NMP_SLOT(sagxy), s.SAG);
+  io.st(NMP_SLOT(rssunxy), o.RSSUN);
+  io.st(NMP_SLOT(rsshaxy), o.RSSHA);
+  io.st(NMP_SLOT(bgapxy), o.BGAP);
+  io.st(NMP_SLOT(wgapxy), o.WGAP);
+  io.st(NMP_SLOT(tgvxy), o.TGV);
+  io.st(NMP_SLOT(tgbxy), o.TGB);
+  io.st(NMP_SLOT(chvxy), o.CHV);
+  io.st(NMP_SLOT(chbxy), o.CHB);
+  io.st(NMP_SLOT(ircxy), o.IRC);
+  io.st(NMP_SLOT(irgxy), o.IRG);
+  io.st(NMP_SLOT(shcxy), o.SHC);
+  io.st(NMP_SLOT(shgxy), o.SHG);
+  io.st(NMP_SLOT(evgxy), o.EVG);
+  io.st(NMP_SLOT(ghvxy), o.GHV);
+  io.st(NMP_SLOT(irbxy), o.IRB);
+  io.st(NMP_SLOT(shbxy), o.SHB);
+  io.st(NMP_SLOT(evbxy), o.EVB);
+  io.st(NMP_SLOT(ghbxy), o.GHB);
+  io.st(NMP_SLOT(trxy), o.TR);
+  io.st(NMP_SLOT(evcxy), o.EVC);
+  io.st(NMP_SLOT(chleafxy), o.CHLEAF);
+  io.st(NMP_SLOT(chucxy), o.CHUC);
+  io.st(NMP_SLOT(chv2xy), o.CHV2);
+  io.st(NMP_SLOT(chb2xy), o.CHB2);
+  io.st(NMP_SLOT(rechxy), io.ld(NMP_SLOT(rechxy)) + o.RECH * 1.E3f);
+  io.st(NMP_SLOT(deeprechxy), io.ld(NMP_SLOT(deeprechxy)) + o.DEEPRECH);
+  io.st(NMP_SLOT(smcwtdxy), o.SMCWTD);
+}
+
+__device__ __forceinline__ void init_ctx(Ctx& c, const StepParams& p) {
+  c.T = p.tables;
+  c.o.dveg = p.opt[0]; c.o.crs = p.opt[1]; c.o.btr = p.opt[2]; c.o.run = p.opt[3]; c.o.sfc = p.opt[4];
+  c.o.frz = p.opt[5]; c.o.inf = p.opt[6]; c.o.rad = p.opt[7]; c.o.alb = p.opt[8]; c.o.snf = p.opt[9];
+  c.o.tbot = p.opt[10]; c.o.stc = p.opt[11];
+  c.err = 0; c.errv = 0.f;
+}
+
+// ---- land columns: REDPRM + NOAHMP_SFLX (noahmpdrv.F90:449-547, :681-714) ---------------------------
+template <class O>
+__global__ void __launch_bounds__(128) land_kernel(const __grid_constant__ StepParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.count) return;
+  const ColumnIO io(p, (long long)p.first + t);
+  Ctx c;
+  init_ctx(c, p);
+  Col s;
+  load_common(io, p, s);
+  s.ICE = 0;
+  int VEGTYP = io.stati(nmpf::ST_IVGTYP);
+  int SOILTYP = io.stati(nmpf::ST_ISLTYP);
+  const int ivg = VEGTYP;
+  s.SHDFAC = io.forc(nmpf::FC_VEGFRA) / 100.f;
+  s.SHDMAX = io.stat(nmpf::ST_VEGMAX) / 100.f;
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) s.SMCEQ(K) = io.ld(NMP_SLOT(smoiseq) + K - 1);
+  s.TV = io.ld(NMP_SLOT(tvxy));
+  s.CANLIQ = io.ld(NMP_SLOT(canliqxy));
+  s.CANICE = io.ld(NMP_SLOT(canicexy));
+  s.EAH = io.ld(NMP_SLOT(eahxy));
+  s.TAH = io.ld(NMP_SLOT(tahxy));
+  s.FWET = io.ld(NMP_SLOT(fwetxy));
+  s.WSLAKE = io.ld(NMP_SLOT(wslakexy));
+  s.ZWT = io.ld(NMP_SLOT(zwtxy));
+  s.WA = io.ld(NMP_SLOT(waxy));
+  s.WT = io.ld(NMP_SLOT(wtxy));
+  s.LFMASS = io.ld(NMP_SLOT(lfmassxy));
+  s.RTMASS = io.ld(NMP_SLOT(rtmassxy));
+  s.STMASS = io.ld(NMP_SLOT(stmassxy));
+  s.WOOD = io.ld(NMP_SLOT(woodxy));
+  s.STBLCP = io.ld(NMP_SLOT(stblcpxy));
+  s.FASTCP = io.ld(NMP_SLOT(fastcpxy));
+  s.LAI = io.ld(NMP_SLOT(xlaixy));
+  s.SAI = io.ld(NMP_SLOT(xsaixy));
+  s.SMCWTD = io.ld(NMP_SLOT(smcwtdxy));
+  s.RECH = 0.f;
+  s.DEEPRECH = 0.f;
+  const float CO2 = 395.e-06f, O2 = 0.209f;
+  s.CO2AIR = CO2 * s.SFCPRS;
+  s.O2AIR = O2 * s.SFCPRS;
+  s.FOLN = 1.0f;
+
+  if (SOILTYP == 14 && io.stat(nmpf::ST_XICE) == 0.f) SOILTYP = 7;
+  if (ivg == p.isurban || ivg == 31 || ivg == 32 || ivg == 33) VEGTYP = p.isurban;
+  if (VEGTYP == 25 || VEGTYP == 26 || VEGTYP == 27) { s.SHDFAC = 0.0f; s.LAI = 0.0f; }
+  s.VEGTYP = VEGTYP;
+  s.URBAN = (VEGTYP == p.isurban);
+
+  if (REDPRM(c, VEGTYP, SOILTYP, 1, s.URBAN)) {
+    report_error(p, io.cell, c.err, c.errv);
+    return;
+  }
+  // every OUT member is assigned by NOAHMP_SFLX before use except on the dveg error path
+  s.PONDING = 0.f; s.PONDING1 = 0.f; s.PONDING2 = 0.f; s.QSNBOT = 0.f; s.FPICE = 0.f;
+  NOAHMP_SFLX<O>(c, s);
+
+  ColumnOut o;
+  o.QFX = s.ECAN + s.EDIR + s.ETRAN;
+  o.LH = s.FCEV + s.FGEV + s.FCTR;
+  o.TV = s.TV; o.CANICE = s.CANICE; o.CANLIQ = s.CANLIQ; o.EAH = s.EAH; o.TAH = s.TAH; o.FWET = s.FWET;
+  o.WSLAKE = s.WSLAKE; o.ZWT = s.ZWT; o.WA = s.WA; o.WT = s.WT; o.LFMASS = s.LFMASS; o.RTMASS = s.RTMASS;
+  o.STMASS = s.STMASS; o.WOOD = s.WOOD; o.STBLCP = s.STBLCP; o.FASTCP = s.FASTCP; o.PLAI = s.LAI; o.PSAI = s.SAI;
+  o.T2MV = s.T2MV; o.T2MB = s.T2MB; o.Q2MV = s.Q2V; o.Q2MB = s.Q2B; o.NEE = s.NEE; o.GPP = s.GPP; o.NPP = s.NPP;
+  o.FVEGMP = s.FVEG; o.ECAN = s.ECAN; o.ETRAN = s.ETRAN; o.ESOIL = s.EDIR; o.APAR = s.APAR; o.PSN = s.PSN;
+  o.SAV = s.SAV; o.RSSUN = s.RSSUN; o.RSSHA = s.RSSHA; o.BGAP = s.BGAP; o.WGAP = s.WGAP; o.TGV = s.TGV;
+  o.TGB = s.TGB; o.CHV = s.CHV; o.CHB = s.CHB; o.IRC = s.IRC; o.IRG = s.IRG; o.SHC = s.SHC; o.SHG = s.SHG;
+  o.EVG = s.EVG; o.GHV = s.GHV; o.IRB = s.IRB; o.SHB = s.SHB; o.EVB = s.EVB; o.GHB = s.GHB; o.TR = s.TR;
+  o.EVC = s.EVC; o.CHLEAF = s.CHLEAF; o.CHUC = s.CHUC; o.CHV2 = s.CHV2; o.CHB2 = s.CHB2; o.FSNO = s.FSNO;
+  o.RECH = s.RECH; o.DEEPRECH = s.DEEPRECH; o.SMCWTD = s.SMCWTD;
+  store_column(io, p, s, o);
+  if (p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
+  if (c.err) report_error(p, io.cell, c.err, c.errv);
+}
+
+// ---- glacier columns: NOAHMP_GLACIER + sentinel fills (noahmpdrv.F90:552-628) ------------------------
+template <class O>
+__global__ void __launch_bounds__(128) glacier_kernel(const __grid_constant__ StepParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.count) return;
+  const ColumnIO io(p, (long long)p.first + t);
+  Ctx c;
+  init_ctx(c, p);
+  Col s;
+  load_common(io, p, s);
+  s.ICE = -1;
+  s.TBOT = MIN(s.TBOT, 263.15f);
+  s.PONDING = 0.f; s.PONDING1 = 0.f; s.PONDING2 = 0.f; s.QSNBOT = 0.f;
+  // REDPRM runs for glacier columns too (noahmpdrv.F90:547); its range checks are the only effect
+  {
+    int VEGTYP = io.stati(nmpf::ST_IVGTYP), SOILTYP = io.stati(nmpf::ST_ISLTYP);
+    if (SOILTYP == 14 && io.stat(nmpf::ST_XICE) == 0.f) SOILTYP = 7;
+    const int ivg = VEGTYP;
+    if (ivg == p.isurban || ivg == 31 || ivg == 32 || ivg == 33) VEGTYP = p.isurban;
+    if (REDPRM(c, VEGTYP, SOILTYP, 1, VEGTYP == p.isurban)) {
+      report_error(p, io.cell, c.err, c.errv);
+      return;
+    }
+  }
+  NOAHMP_GLACIER<O>(c, s);
+
+  const float U1 = -1.E36f, U2 = 0.0f;  // undefined_value / undefined_value2 (noahmpdrv.F90:368-369)
+  ColumnOut o;
+  o.QFX = s.EDIR;
+  o.LH = s.FGEV;
+  o.FSNO = 1.0f;
+  o.TV = U1; o.TGB = s.TG; o.CANICE = U2; o.CANLIQ = U2; o.EAH = U1; o.TAH = U1; o.FWET = U2; o.WSLAKE = U2;
+  o.ZWT = U1; o.WA = U1; o.WT = U1; o.LFMASS = U2; o.RTMASS = U2; o.STMASS = U2; o.WOOD = U2; o.STBLCP = U1;
+  o.FASTCP = U1; o.PLAI = U2; o.PSAI = U2; o.T2MV = U1; o.Q2MV = U1; o.NEE = U2; o.GPP = U2; o.NPP = U2;
+  o.FVEGMP = 0.0f; o.ECAN = U2; o.ETRAN = U2; o.APAR = U2; o.PSN = U2; o.SAV = U2; o.RSSUN = U1; o.RSSHA = U1;
+  o.BGAP = U1; o.WGAP = U1; o.TGV = U1; o.CHV = U1; o.CHB = s.CH; o.IRC = U1; o.IRG = U1; o.SHC = U1; o.SHG = U1;
+  o.EVG = U1; o.GHV = U1; o.IRB = s.FIRA; o.SHB = s.FSH; o.EVB = s.FGEV; o.GHB = s.SSOIL; o.TR = U2; o.EVC = U2;
+  o.CHLEAF = U1; o.CHUC = U1; o.CHV2 = U1; o.CHB2 = s.CHB2;
+  o.T2MB = s.T2MB; o.Q2MB = s.Q2B; o.ESOIL = s.EDIR;
+  o.RECH = 0.f; o.DEEPRECH = 0.f;
+  o.SMCWTD = io.ld(NMP_SLOT(smcwtdxy));
+  store_column(io, p, s, o);
+  if (p.vege_iters) p.vege_iters[io.cell] = 0;
+  if (c.err) report_error(p, io.cell, c.err, c.errv);
+}
+
+template <class O>
+void launch_pair(const StepParams& base, int nland, int nglac, cudaStream_t stream, long long* launches) {
+  if (nland > 0) {
+    StepParams p = base;
+    p.first = 0;
+    p.count = nland;
+    land_kernel<O><<<(nland + 127) / 128, 128, 0, stream>>>(p);
+    ++*launches;
+  }
+  if (nglac > 0) {
+    StepParams p = base;
+    p.first = nland;
+    p.count = nglac;
+    glacier_kernel<O><<<(nglac + 127) / 128, 128, 0, stream>>>(p);
+    ++*launches;
+  }
+}
+
+// compile-time option sets: dveg crs btr run sfc frz inf rad alb snf tbot stc
+using OptDefault = OptSet<4, 1, 1, 1, 1, 1, 1, 3, 2, 1, 2, 1>;  // BASELINE configs C1/C2/C4
+using OptDynVeg = OptSet<2, 1, 1, 1, 1, 1, 1, 3, 2, 1, 2, 1>;   // C3: dveg=2 dynamic vegetation
+
+template <class O>
+bool matches(const int* opt) {
+  const int want[12] = {O::dveg, O::crs, O::btr, O::run, O::sfc, O::frz, O::inf, O::rad, O::alb, O::snf, O::tbot,
+                        O::stc};
+  for (int k = 0; k < 12; ++k)
+    if (want[k] != opt[k]) return false;
+  return true;
+}
+
+// Picks the specialised instantiation when the namelist options match one, else the generic kernel that
+// reads the options at run time.  Returns the name of the variant (for logs / tests).
+const char* launch_step(const StepParams& base, int nland, int nglac, cudaStream_t stream, long long* launches) {
+#ifndef NMP_NO_SPECIALISE
+  if (getenv("NOAHMP_B200_FORCE_RUNTIME")) {
+    launch_pair<OptRuntime>(base, nland, nglac, stream, launches);
+    return "runtime";
+  }
+  if (matches<OptDefault>(base.opt)) { launch_pair<OptDefault>(base, nland, nglac, stream, launches); return "default"; }
+  if (matches<OptDynVeg>(base.opt)) { launch_pair<OptDynVeg>(base, nland, nglac, stream, launches); return "dynveg"; }
+#endif
+  launch_pair<OptRuntime>(base, nland, nglac, stream, launches);
+  return "runtime";
+}
+
+}  // namespace

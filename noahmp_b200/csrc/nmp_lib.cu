@@ -1,0 +1,734 @@
+// nmp_lib.cu — host side of libnoahmp_b200.so: the C-ABI of include/noahmp_b200.h.
+//
+// Replaces the grid loop of `noahmplsm` (phys/module_sf_noahmpdrv.F90:376-840): classification of cells
+// into water / land / glacier / sea-ice (:426-441), the ITIMESTEP==1 initialisation of water and sea-ice
+// rows (:399-419), the per-column gather/scatter (:449-512, :728-835) and the status convention that
+// stands in for wrf_error_fatal.  There is no CPU fallback: without a CUDA device create() fails.
+#include <cuda_runtime.h>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "nmp_fields.h"
+
+using namespace nmpf;
+
+// launchers of the two physics builds (nmp_kernels_fast.cu / nmp_kernels_parity.cu)
+const char* nmp_launch_step_fast(const StepParams& base, int nland, int nglac, cudaStream_t stream,
+                                 long long* launches);
+const char* nmp_launch_step_parity(const StepParams& base, int nland, int nglac, cudaStream_t stream,
+                                   long long* launches);
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+      return NOAHMP_ERR_CUDA;                                                                        \
+    }                                                                                                \
+  } while (0)
+
+// ---- field table: host pointer of every state field inside noahmp_lsm_args ---------------------------
+struct FieldInfo {
+  const char* name;
+  size_t arg_offset;
+  int layers, kind, slot;
+};
+static const FieldInfo kFields[NFIELDS] = {
+#define X(nm, nl, k) {#nm, offsetof(noahmp_lsm_args, nm), nl, k, 0},
+    NMP_STATE_FIELDS(X)
+#undef X
+};
+static inline float* host_ptr(const noahmp_lsm_args* a, int f) {
+  return *reinterpret_cast<float* const*>(reinterpret_cast<const char*>(a) + kFields[f].arg_offset);
+}
+
+// descriptor of one (field, layer) plane for the batched gather / scatter kernels
+struct PlaneDesc {
+  float* grid;     // staging array of the field, Fortran (i,k,j) layout
+  int plane;       // plane index in the compact state
+  int layer, layers;
+};
+
+struct noahmp_b200_ctx {
+  int device = 0, ni = 0, nj = 0;
+  long long ncell = 0;
+  cudaStream_t stream = nullptr;
+  noahmp_tables* d_tables = nullptr;
+  float* d_forc[NFORC] = {};
+  float* d_stat[NSTATIC] = {};
+  float* d_state = nullptr;
+  long long np = 0, np_alloc = 0;
+  float* d_grid[NFIELDS] = {};
+  bool grid_init[NFIELDS] = {};
+  PlaneDesc* d_planes = nullptr;
+  int nplanes_desc = 0;
+  int* d_cell = nullptr;
+  unsigned char* d_class = nullptr;
+  void* d_cub = nullptr;
+  size_t cub_bytes = 0;
+  int* d_nsel = nullptr;
+  int nclass[4] = {0, 0, 0, 0};  // water, land, glacier, seaice
+  unsigned long long* d_errkey = nullptr;
+  int* d_errcount = nullptr;
+  unsigned long long* h_errkey = nullptr;  // pinned
+  int* h_errcount = nullptr;
+  int* d_vege_iters = nullptr;
+  int sync_mode = NOAHMP_SYNC_FULL;
+  int math_mode = 0;
+  bool uploaded = false, classified = false;
+  bool pin_host = true;
+  StepParams base{};
+  long long launches = 0;
+  std::string variant;
+  std::unordered_map<const void*, size_t> registered;
+};
+
+// ---- small kernels ------------------------------------------------------------------------------------
+// noahmpdrv.F90:426-441
+__global__ void classify_kernel(const float* __restrict__ xland, const float* __restrict__ xice,
+                                const float* __restrict__ ivgtyp_bits, float xice_thres, int isice, long long ncell,
+                                unsigned char* __restrict__ cls) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int ICE;
+  if (xice[c] >= xice_thres) ICE = 1;
+  else if (__float_as_int(ivgtyp_bits[c]) == isice) ICE = -1;
+  else ICE = 0;
+  unsigned char k;
+  if ((xland[c] - 1.5f) >= 0.f) k = CL_WATER;
+  else if (ICE == 1) k = CL_SEAICE;
+  else if (ICE == -1) k = CL_GLACIER;
+  else k = CL_LAND;
+  cls[c] = k;
+}
+
+struct ClassIs {
+  const unsigned char* cls;
+  unsigned char want;
+  __host__ __device__ bool operator()(int c) const { return cls[c] == want; }
+};
+
+// grid order (Fortran (i,k,j)) <-> compact planes; blockIdx.y = plane descriptor
+__global__ void gather_kernel(const PlaneDesc* __restrict__ planes, const int* __restrict__ cell, float* state,
+                              long long np, int ni) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  const PlaneDesc d = planes[blockIdx.y];
+  const int c = cell[n];
+  const int i = c % ni, j = c / ni;
+  state[(long long)d.plane * np + n] = d.grid[(long long)i + (long long)d.layer * ni + (long long)j * ni * d.layers];
+}
+__global__ void scatter_kernel(const PlaneDesc* __restrict__ planes, const int* __restrict__ cell,
+                               const float* __restrict__ state, long long np, int ni) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  const PlaneDesc d = planes[blockIdx.y];
+  const int c = cell[n];
+  const int i = c % ni, j = c / ni;
+  d.grid[(long long)i + (long long)d.layer * ni + (long long)j * ni * d.layers] = state[(long long)d.plane * np + n];
+}
+
+// ITIMESTEP == 1 initialisation of open-water and full sea-ice cells (noahmpdrv.F90:399-419); works on the
+// grid-order staging arrays because those cells have no compact column.
+__global__ void first_step_water_kernel(const float* __restrict__ xland, const float* __restrict__ xice, float* smstav,
+                                        float* smstot, float* smois, float* tslb, int ni, long long ncell) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int i = (int)(c % ni);
+  const long long j = c / ni;
+  if ((xland[c] - 1.5f) >= 0.f) {
+    smstav[c] = 1.0f;
+    smstot[c] = 1.0f;
+    for (int k = 0; k < NOAHMP_NSOIL; ++k) {
+      smois[i + (long long)k * ni + j * ni * NOAHMP_NSOIL] = 1.0f;
+      tslb[i + (long long)k * ni + j * ni * NOAHMP_NSOIL] = 273.16f;
+    }
+  } else if (xice[c] == 1.f) {
+    smstav[c] = 1.0f;
+    smstot[c] = 1.0f;
+    for (int k = 0; k < NOAHMP_NSOIL; ++k) smois[i + (long long)k * ni + j * ni * NOAHMP_NSOIL] = 1.0f;
+  }
+}
+
+// sea-ice columns: SH2O = 1, XLAI = 0.01 (noahmpdrv.F90:436-441)
+__global__ void seaice_kernel(float* state, long long np, int first, int count) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  long long n = (long long)first + t;
+  for (int k = 0; k < NOAHMP_NSOIL; ++k) state[(long long)(NMP_SLOT(sh2o) + k) * np + n] = 1.0f;
+  state[(long long)NMP_SLOT(xlaixy) * np + n] = 0.01f;
+}
+
+// ---- helpers ------------------------------------------------------------------------------------------
+static void pin(noahmp_b200_ctx* ctx, const void* p, size_t bytes) {
+  if (!ctx->pin_host || !p || !bytes) return;
+  auto it = ctx->registered.find(p);
+  if (it != ctx->registered.end() && it->second >= bytes) return;
+  if (it != ctx->registered.end()) cudaHostUnregister(const_cast<void*>(p));
+  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+  if (e == cudaSuccess) ctx->registered[p] = bytes;
+  else {
+    cudaGetLastError();         // already pinned by the caller, or not pinnable: plain pageable copy
+    ctx->registered[p] = 0;     // remember not to retry every call
+    if (e == cudaErrorHostMemoryAlreadyRegistered) ctx->registered[p] = bytes;
+  }
+}
+static void unpin_all(noahmp_b200_ctx* ctx) {
+  for (auto& kv : ctx->registered)
+    if (kv.second) { if (cudaHostUnregister(const_cast<void*>(kv.first)) != cudaSuccess) cudaGetLastError(); }
+  ctx->registered.clear();
+}
+
+static int check_bounds(const noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  // HRLDAS allocates exactly the tile: ims=its ... (driver/module_hrldas_noahmp_driver.F90:112-129)
+  if (a->ims != a->its || a->ime != a->ite || a->jms != a->jts || a->jme != a->jte) {
+    set_error("memory bounds must equal tile bounds (ims=its, ime=ite, jms=jts, jme=jte) as in HRLDAS");
+    return NOAHMP_ERR_ARG;
+  }
+  if (a->ite - a->its + 1 != ctx->ni || a->jte - a->jts + 1 != ctx->nj) {
+    set_error("tile extent differs from the context's ni x nj");
+    return NOAHMP_ERR_ARG;
+  }
+  if (a->nsoil != NOAHMP_NSOIL) { set_error("nsoil must be 4"); return NOAHMP_ERR_ARG; }
+  if (a->kme - a->kms + 1 < 2 || a->kms > 1 || a->kme < 2 || a->kts != 1) {
+    set_error("vertical bounds must contain levels 1 and 2 with kts=1");
+    return NOAHMP_ERR_ARG;
+  }
+  return 0;
+}
+
+static void fill_scalars(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  StepParams& b = ctx->base;
+  b.dx = a->dx;
+  b.xice_thres = a->xice_thres;
+  b.isice = a->isice;
+  b.isurban = a->isurban;
+  b.iz0tlnd = a->iz0tlnd;
+  // ZSOIL (noahmpdrv.F90:392-395)
+  b.zsoil[0] = -a->dzs[0];
+  for (int k = 1; k < NOAHMP_NSOIL; ++k) b.zsoil[k] = -a->dzs[k] + b.zsoil[k - 1];
+  const int o[12] = {a->idveg,    a->iopt_crs, a->iopt_btr, a->iopt_run, a->iopt_sfc,  a->iopt_frz,
+                     a->iopt_inf, a->iopt_rad, a->iopt_alb, a->iopt_snf, a->iopt_tbot, a->iopt_stc};
+  for (int k = 0; k < 12; ++k) b.opt[k] = o[k];
+}
+
+static int year_length(int yr) {  // noahmpdrv.F90:381-390
+  int YEARLEN = 365;
+  if (yr % 4 == 0) {
+    YEARLEN = 366;
+    if (yr % 100 == 0) {
+      YEARLEN = 365;
+      if (yr % 400 == 0) YEARLEN = 366;
+    }
+  }
+  return YEARLEN;
+}
+
+static int check_options(const noahmp_b200_ctx* ctx) {
+  const int* o = ctx->base.opt;
+  const int lo[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+  const int hi[12] = {5, 2, 3, 5, 2, 2, 2, 3, 2, 3, 2, 2};
+  static const char* nm[12] = {"dveg", "opt_crs", "opt_btr", "opt_run", "opt_sfc", "opt_frz",
+                               "opt_inf", "opt_rad", "opt_alb", "opt_snf", "opt_tbot", "opt_stc"};
+  for (int k = 0; k < 12; ++k) {
+    if (o[k] < lo[k] || o[k] > hi[k]) {
+      // opt_sfc 3/4 (MYJ / YSU) read lookup tables nothing initialises offline
+      set_error(std::string("unsupported option value for ") + nm[k]);
+      return NOAHMP_ERR_OPTION;
+    }
+  }
+  return 0;
+}
+
+static int ensure_grid(noahmp_b200_ctx* ctx, int f) {
+  if (!ctx->d_grid[f]) {
+    CK(cudaMalloc(&ctx->d_grid[f], sizeof(float) * ctx->ncell * kFields[f].layers));
+    CK(cudaMemsetAsync(ctx->d_grid[f], 0, sizeof(float) * ctx->ncell * kFields[f].layers, ctx->stream));
+    // descriptors must be refreshed
+    ctx->nplanes_desc = 0;
+  }
+  return 0;
+}
+
+static int build_plane_descs(noahmp_b200_ctx* ctx) {
+  if (ctx->nplanes_desc == NPLANES) return 0;
+  std::vector<PlaneDesc> h;
+  for (int f = 0; f < NFIELDS; ++f) {
+    int rc = ensure_grid(ctx, f);
+    if (rc) return rc;
+    for (int k = 0; k < kFields[f].layers; ++k) h.push_back({ctx->d_grid[f], kSlots.slot[f] + k, k, kFields[f].layers});
+  }
+  if (!ctx->d_planes) CK(cudaMalloc(&ctx->d_planes, sizeof(PlaneDesc) * NPLANES));
+  CK(cudaMemcpyAsync(ctx->d_planes, h.data(), sizeof(PlaneDesc) * NPLANES, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->nplanes_desc = NPLANES;
+  return 0;
+}
+
+// H2D of one 2-D plane; for 3-D atmospheric arrays (i,k,j) picks level `lev` (1-based)
+static int h2d_plane(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, int kms, int lev) {
+  const size_t ni = ctx->ni, nj = ctx->nj;
+  if (nk == 1) {
+    pin(ctx, src, sizeof(float) * ni * nj);
+    CK(cudaMemcpyAsync(dst, src, sizeof(float) * ni * nj, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    pin(ctx, src, sizeof(float) * ni * nj * nk);
+    CK(cudaMemcpy2DAsync(dst, sizeof(float) * ni, src + (size_t)(lev - kms) * ni, sizeof(float) * ni * nk,
+                         sizeof(float) * ni, nj, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return 0;
+}
+
+static int upload_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  const int nk = a->kme - a->kms + 1, kms = a->kms;
+  int rc = 0;
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_COSZIN], a->coszin, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_T], a->t3d, nk, kms, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_QV], a->qv3d, nk, kms, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_U], a->u_phy, nk, kms, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_V], a->v_phy, nk, kms, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_SWDOWN], a->swdown, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_GLW], a->glw, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_P1], a->p8w3d, nk, kms, a->kts);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_P2], a->p8w3d, nk, kms, a->kts + 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_RAINBL], a->rainbl, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_VEGFRA], a->vegfra, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_forc[FC_DZ8W], a->dz8w, nk, kms, 1);
+  return rc ? NOAHMP_ERR_CUDA : 0;
+}
+
+static int upload_static(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  int rc = 0;
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_IVGTYP], reinterpret_cast<const float*>(a->ivgtyp), 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_ISLTYP], reinterpret_cast<const float*>(a->isltyp), 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_VEGMAX], a->vegmax, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_TMN], a->tmn, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_XLATIN], a->xlatin, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_XLAND], a->xland, 1, 1, 1);
+  rc |= h2d_plane(ctx, ctx->d_stat[ST_XICE], a->xice, 1, 1, 1);
+  return rc ? NOAHMP_ERR_CUDA : 0;
+}
+
+// cell classification + stable compaction: land | glacier | sea-ice, each in grid order
+static int classify(noahmp_b200_ctx* ctx) {
+  const long long nc = ctx->ncell;
+  const int T = 256;
+  classify_kernel<<<(unsigned)((nc + T - 1) / T), T, 0, ctx->stream>>>(
+      ctx->d_stat[ST_XLAND], ctx->d_stat[ST_XICE], ctx->d_stat[ST_IVGTYP], ctx->base.xice_thres, ctx->base.isice, nc,
+      ctx->d_class);
+  ctx->launches++;
+  thrust::counting_iterator<int> it(0);
+  const unsigned char order[3] = {CL_LAND, CL_GLACIER, CL_SEAICE};
+  int offset = 0;
+  for (int k = 0; k < 3; ++k) {
+    ClassIs pred{ctx->d_class, order[k]};
+    size_t need = 0;
+    CK(cub::DeviceSelect::If(nullptr, need, it, ctx->d_cell + offset, ctx->d_nsel, (int)nc, pred, ctx->stream));
+    if (need > ctx->cub_bytes) {
+      if (ctx->d_cub) CK(cudaFree(ctx->d_cub));
+      CK(cudaMalloc(&ctx->d_cub, need));
+      ctx->cub_bytes = need;
+    }
+    CK(cub::DeviceSelect::If(ctx->d_cub, need, it, ctx->d_cell + offset, ctx->d_nsel, (int)nc, pred, ctx->stream));
+    int nsel = 0;
+    CK(cudaMemcpyAsync(&nsel, ctx->d_nsel, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nclass[order[k]] = nsel;
+    offset += nsel;
+  }
+  ctx->np = offset;
+  ctx->nclass[CL_WATER] = (int)(nc - offset);
+  if (ctx->np > ctx->np_alloc) {
+    if (ctx->d_state) CK(cudaFree(ctx->d_state));
+    CK(cudaMalloc(&ctx->d_state, sizeof(float) * (size_t)NPLANES * (size_t)ctx->np));
+    ctx->np_alloc = ctx->np;
+  }
+  ctx->classified = true;
+  return 0;
+}
+
+static int gather_fields(noahmp_b200_ctx* ctx) {
+  if (ctx->np == 0) return 0;
+  const int T = 256;
+  dim3 grid((unsigned)((ctx->np + T - 1) / T), NPLANES);
+  gather_kernel<<<grid, T, 0, ctx->stream>>>(ctx->d_planes, ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int scatter_fields(noahmp_b200_ctx* ctx) {
+  if (ctx->np == 0) return 0;
+  const int T = 256;
+  dim3 grid((unsigned)((ctx->np + T - 1) / T), NPLANES);
+  scatter_kernel<<<grid, T, 0, ctx->stream>>>(ctx->d_planes, ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// H2D of the state arrays into staging; `all` also brings the OUT arrays (needed once so that untouched
+// water cells keep the caller's values on the way back)
+static int upload_state(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, bool all) {
+  for (int f = 0; f < NFIELDS; ++f) {
+    const bool want = kFields[f].kind == NMP_K_INOUT || all || !ctx->grid_init[f];
+    if (!want) continue;
+    const float* src = host_ptr(a, f);
+    if (!src) { set_error(std::string("null array: ") + kFields[f].name); return NOAHMP_ERR_ARG; }
+    const size_t bytes = sizeof(float) * ctx->ncell * kFields[f].layers;
+    pin(ctx, src, bytes);
+    CK(cudaMemcpyAsync(ctx->d_grid[f], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->grid_init[f] = true;
+  }
+  return 0;
+}
+
+static int download_state(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  for (int f = 0; f < NFIELDS; ++f) {
+    if (f == F_smoiseq) continue;  // INTENT(IN) in effect: never written by noahmplsm
+    float* dst = host_ptr(a, f);
+    const size_t bytes = sizeof(float) * ctx->ncell * kFields[f].layers;
+    pin(ctx, dst, bytes);
+    CK(cudaMemcpyAsync(dst, ctx->d_grid[f], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return 0;
+}
+
+static void decode_status(noahmp_b200_ctx* ctx, noahmp_status* st) {
+  if (!st) return;
+  st->code = 0; st->i = 0; st->j = 0; st->count = *ctx->h_errcount; st->value = 0.f;
+  if (*ctx->h_errcount > 0) {
+    const unsigned long long key = *ctx->h_errkey;
+    const unsigned cell = (unsigned)(key >> 39);
+    st->code = (int)((key >> 32) & 0x7f);
+    unsigned vb = (unsigned)(key & 0xffffffffu);
+    memcpy(&st->value, &vb, 4);
+    st->i = (int)(cell % (unsigned)ctx->ni) + 1;
+    st->j = (int)(cell / (unsigned)ctx->ni) + 1;
+  }
+}
+
+// ---- C ABI ----------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* noahmp_b200_last_error(void) { return g_last_error.c_str(); }
+
+noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int ni, int nj) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (this library has no CPU fallback)");
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev || !tables || ni <= 0 || nj <= 0 || (long long)ni * nj >= (1LL << 25)) {
+    set_error("bad arguments to noahmp_b200_create (need 0 < ni*nj < 2^25 per tile)");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10) {
+    set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+              "; this library carries sm_100a code only");
+    return nullptr;
+  }
+  auto* ctx = new noahmp_b200_ctx();
+  ctx->device = device; ctx->ni = ni; ctx->nj = nj; ctx->ncell = (long long)ni * nj;
+  const char* env = getenv("NOAHMP_B200_MATH");
+  if (env && (!strcmp(env, "parity") || !strcmp(env, "1"))) ctx->math_mode = 1;
+  env = getenv("NOAHMP_B200_PIN");
+  if (env && !strcmp(env, "0")) ctx->pin_host = false;
+  bool ok = true;
+  auto A = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false; };
+  ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  A((void**)&ctx->d_tables, sizeof(noahmp_tables));
+  for (int f = 0; f < NFORC; ++f) A((void**)&ctx->d_forc[f], sizeof(float) * ctx->ncell);
+  for (int f = 0; f < NSTATIC; ++f) A((void**)&ctx->d_stat[f], sizeof(float) * ctx->ncell);
+  A((void**)&ctx->d_cell, sizeof(int) * ctx->ncell);
+  A((void**)&ctx->d_class, ctx->ncell);
+  A((void**)&ctx->d_nsel, sizeof(int));
+  A((void**)&ctx->d_errkey, sizeof(unsigned long long));
+  A((void**)&ctx->d_errcount, sizeof(int));
+  if (ok) ok = cudaMallocHost((void**)&ctx->h_errkey, sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) ok = cudaMallocHost((void**)&ctx->h_errcount, sizeof(int)) == cudaSuccess;
+  if (ok) ok = cudaMemcpy(ctx->d_tables, tables, sizeof(noahmp_tables), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) {
+    set_error(std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    noahmp_b200_destroy(ctx);
+    return nullptr;
+  }
+  *ctx->h_errcount = 0;
+  *ctx->h_errkey = 0;
+  StepParams& b = ctx->base;
+  for (int f = 0; f < NFORC; ++f) b.forc[f] = ctx->d_forc[f];
+  for (int f = 0; f < NSTATIC; ++f) b.stat[f] = ctx->d_stat[f];
+  b.tables = ctx->d_tables;
+  b.err_key = ctx->d_errkey;
+  b.err_count = ctx->d_errcount;
+  b.vege_iters = nullptr;
+  b.ni = ni;
+  return ctx;
+}
+
+void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  unpin_all(ctx);
+  cudaFree(ctx->d_tables);
+  for (auto p : ctx->d_forc) cudaFree(p);
+  for (auto p : ctx->d_stat) cudaFree(p);
+  for (auto p : ctx->d_grid) cudaFree(p);
+  cudaFree(ctx->d_state); cudaFree(ctx->d_planes); cudaFree(ctx->d_cell); cudaFree(ctx->d_class);
+  cudaFree(ctx->d_cub); cudaFree(ctx->d_nsel); cudaFree(ctx->d_errkey); cudaFree(ctx->d_errcount);
+  cudaFree(ctx->d_vege_iters);
+  if (ctx->h_errkey) cudaFreeHost(ctx->h_errkey);
+  if (ctx->h_errcount) cudaFreeHost(ctx->h_errcount);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
+  delete ctx;
+}
+
+int noahmp_b200_set_mode(noahmp_b200_ctx* ctx, int sync_mode) {
+  if (!ctx || (sync_mode != NOAHMP_SYNC_FULL && sync_mode != NOAHMP_SYNC_RESIDENT)) return NOAHMP_ERR_ARG;
+  ctx->sync_mode = sync_mode;
+  return 0;
+}
+
+int noahmp_b200_set_math(noahmp_b200_ctx* ctx, int math_mode) {
+  if (!ctx || (math_mode != NOAHMP_MATH_FAST && math_mode != NOAHMP_MATH_PARITY)) return NOAHMP_ERR_ARG;
+  ctx->math_mode = math_mode;
+  return 0;
+}
+
+const char* noahmp_b200_kernel_variant(const noahmp_b200_ctx* ctx) { return ctx ? ctx->variant.c_str() : ""; }
+
+int noahmp_b200_upload(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  if (!ctx || !a) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_bounds(ctx, a);
+  if (rc) return rc;
+  fill_scalars(ctx, a);
+  if ((rc = check_options(ctx))) return rc;
+  if ((rc = build_plane_descs(ctx))) return rc;
+  if ((rc = upload_static(ctx, a))) return rc;
+  if ((rc = upload_forcing(ctx, a))) return rc;
+  if ((rc = classify(ctx))) return rc;
+  if ((rc = upload_state(ctx, a, /*all=*/!ctx->uploaded))) return rc;
+  if ((rc = gather_fields(ctx))) return rc;
+  ctx->base.state = ctx->d_state;
+  ctx->base.cell = ctx->d_cell;
+  ctx->base.np = ctx->np;
+  ctx->uploaded = true;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int noahmp_b200_device_forcing(noahmp_b200_ctx* ctx, float** dev_ptrs) {
+  if (!ctx || !dev_ptrs) return NOAHMP_ERR_ARG;
+  for (int f = 0; f < NFORC; ++f) dev_ptrs[f] = ctx->d_forc[f];
+  return 0;
+}
+
+int noahmp_b200_enable_iteration_counts(noahmp_b200_ctx* ctx, int enable) {
+  if (!ctx) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (enable && !ctx->d_vege_iters) {
+    CK(cudaMalloc(&ctx->d_vege_iters, sizeof(int) * ctx->ncell));
+    CK(cudaMemset(ctx->d_vege_iters, 0, sizeof(int) * ctx->ncell));
+  }
+  ctx->base.vege_iters = enable ? ctx->d_vege_iters : nullptr;
+  return 0;
+}
+int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out) {
+  if (!ctx || !out || !ctx->d_vege_iters) return NOAHMP_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d_vege_iters, sizeof(int) * ctx->ncell, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt, void* stream) {
+  if (!ctx || !ctx->uploaded) { set_error("step_device before upload"); return NOAHMP_ERR_ARG; }
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  StepParams p = ctx->base;
+  p.itimestep = itimestep;
+  p.yearlen = year_length(yr);
+  p.julian = julian;
+  p.dt = dt;
+  CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), s));
+  if (itimestep == 1 && ctx->nclass[CL_WATER] + ctx->nclass[CL_SEAICE] > 0) {
+    const int T = 256;
+    first_step_water_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, s>>>(
+        ctx->d_stat[ST_XLAND], ctx->d_stat[ST_XICE], ctx->d_grid[F_smstav], ctx->d_grid[F_smstot],
+        ctx->d_grid[F_smois], ctx->d_grid[F_tslb], ctx->ni, ctx->ncell);
+    ctx->launches++;
+  }
+  const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
+  const char* v = ctx->math_mode == NOAHMP_MATH_PARITY ? nmp_launch_step_parity(p, nland, nglac, s, &ctx->launches)
+                                                       : nmp_launch_step_fast(p, nland, nglac, s, &ctx->launches);
+  ctx->variant = v;
+  if (nsea > 0) {
+    seaice_kernel<<<(nsea + 255) / 256, 256, 0, s>>>(ctx->d_state, ctx->np, nland + nglac, nsea);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int noahmp_b200_get_status(noahmp_b200_ctx* ctx, noahmp_status* status) {
+  if (!ctx) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(ctx->h_errkey, ctx->d_errkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ctx->h_errcount, ctx->d_errcount, sizeof(int), cudaMemcpyDeviceToHost));
+  decode_status(ctx, status);
+  return status ? status->code : 0;
+}
+
+int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  if (!ctx || !a || !ctx->uploaded) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_bounds(ctx, a);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());  // steps may have been issued on a caller stream
+  if ((rc = scatter_fields(ctx))) return rc;
+  if ((rc = download_state(ctx, a))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp_status* status) {
+  if (!ctx || !a) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if (ctx->sync_mode == NOAHMP_SYNC_FULL || !ctx->uploaded) {
+    if ((rc = noahmp_b200_upload(ctx, a))) { if (status) { status->code = rc; status->count = 0; } return rc; }
+  } else {
+    if ((rc = check_bounds(ctx, a))) return rc;
+    fill_scalars(ctx, a);
+    if ((rc = check_options(ctx))) return rc;
+    if ((rc = upload_forcing(ctx, a))) return rc;
+  }
+  if ((rc = noahmp_b200_step_device(ctx, a->itimestep, a->yr, a->julian, a->dt, nullptr))) return rc;
+  if (ctx->sync_mode == NOAHMP_SYNC_FULL) {
+    if ((rc = scatter_fields(ctx))) return rc;
+    if ((rc = download_state(ctx, a))) return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->h_errkey, ctx->d_errkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_errcount, ctx->d_errcount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  noahmp_status st;
+  decode_status(ctx, &st);
+  if (status) *status = st;
+  return st.code;
+}
+
+// Refresh ONE host array from HBM (e.g. TSK / HFX / LH after a RESIDENT-mode step; the HRLDAS driver prints
+// TSLB(1,1,1) and LAI(1,1) every step, module_hrldas_noahmp_driver.F90:567-572).
+int noahmp_b200_fetch(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, const char* field) {
+  if (!ctx || !a || !field || !ctx->uploaded) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int f = 0;
+  for (; f < NFIELDS; ++f)
+    if (!strcmp(field, kFields[f].name)) break;
+  if (f == NFIELDS) { set_error(std::string("unknown field ") + field); return NOAHMP_ERR_ARG; }
+  if (ctx->np > 0) {
+    const int T = 256;
+    dim3 grid((unsigned)((ctx->np + T - 1) / T), kFields[f].layers);
+    scatter_kernel<<<grid, T, 0, ctx->stream>>>(ctx->d_planes + kSlots.slot[f], ctx->d_cell, ctx->d_state, ctx->np,
+                                                 ctx->ni);
+    ctx->launches++;
+  }
+  float* dst = host_ptr(a, f);
+  const size_t bytes = sizeof(float) * ctx->ncell * kFields[f].layers;
+  pin(ctx, dst, bytes);
+  CK(cudaMemcpyAsync(dst, ctx->d_grid[f], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Point the step at caller-owned device forcing planes (same order and layout as device_forcing()); NULL
+// restores the context's own staging planes.  Lets a driver keep several forcing hours resident in HBM.
+int noahmp_b200_bind_forcing(noahmp_b200_ctx* ctx, float* const* dev_ptrs) {
+  if (!ctx) return NOAHMP_ERR_ARG;
+  for (int f = 0; f < NFORC; ++f) ctx->base.forc[f] = dev_ptrs ? dev_ptrs[f] : ctx->d_forc[f];
+  return 0;
+}
+
+long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int noahmp_b200_census(const noahmp_b200_ctx* ctx, int64_t counts[4]) {
+  if (!ctx || !ctx->classified) return NOAHMP_ERR_ARG;
+  counts[0] = ctx->nclass[CL_LAND];
+  counts[1] = ctx->nclass[CL_GLACIER];
+  counts[2] = ctx->nclass[CL_SEAICE];
+  counts[3] = ctx->nclass[CL_WATER];
+  return 0;
+}
+
+// compact column -> 0-based tile-local cell index map (land | glacier | sea-ice), for tests and drivers
+int noahmp_b200_column_map(noahmp_b200_ctx* ctx, int32_t* cells, long long capacity) {
+  if (!ctx || !ctx->classified || !cells || capacity < ctx->np) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(cells, ctx->d_cell, sizeof(int) * ctx->np, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Device pointer of plane `layer` of a state field in the compact SoA (np words); NULL if unknown.
+float* noahmp_b200_device_state(noahmp_b200_ctx* ctx, const char* field, int layer, long long* np) {
+  if (!ctx || !ctx->uploaded || !field) return nullptr;
+  for (int f = 0; f < NFIELDS; ++f) {
+    if (!strcmp(field, kFields[f].name)) {
+      if (layer < 0 || layer >= kFields[f].layers) return nullptr;
+      if (np) *np = ctx->np;
+      return ctx->d_state + (size_t)(kSlots.slot[f] + layer) * (size_t)ctx->np;
+    }
+  }
+  return nullptr;
+}
+
+// ---- domain decomposition (mpp/module_mpp_land.F90:124-141, :245-288) -----------------------------------
+void noahmp_b200_proc_grid(int nproc, int* nprocx, int* nprocy) {
+  // mpp_land_get_nprocsxy: over j = 1..nproc with nproc % j == 0, take (nx = nproc/j, ny = j) whenever it
+  // strictly lowers |nx - ny|; the running minimum starts at nproc.
+  int best = nproc, bx = nproc, by = 1;
+  for (int j = 1; j <= nproc; ++j) {
+    if (nproc % j == 0) {
+      int i = nproc / j;
+      int d = i > j ? i - j : j - i;
+      if (d < best) { best = d; bx = i; by = j; }
+    }
+  }
+  *nprocx = bx;
+  *nprocy = by;
+}
+
+void noahmp_b200_tile(int global_nx, int global_ny, int nproc, int rank, int* xstart, int* xend, int* ystart,
+                      int* yend) {
+  int npx, npy;
+  noahmp_b200_proc_grid(nproc, &npx, &npy);
+  const int ipx = rank % npx, ipy = rank / npx;
+  auto split = [](int n, int np, int ip, int* s, int* e) {
+    const int base = n / np, rem = n % np;
+    const int len = base + (ip < rem ? 1 : 0);
+    int start = 1;
+    for (int k = 0; k < ip; ++k) start += base + (k < rem ? 1 : 0);
+    *s = start;
+    *e = start + len - 1;
+  };
+  split(global_nx, npx, ipx, xstart, xend);
+  split(global_ny, npy, ipy, ystart, yend);
+}
+
+}  // extern "C"

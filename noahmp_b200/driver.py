@@ -1,0 +1,168 @@
+"""Host-side driver over the C-ABI: the Python mirror of the reference's `noahmplsm` call.
+
+Arrays use the reference's Fortran memory layout, expressed as C-contiguous numpy arrays of shape
+(nj[, k], ni) (see _capi.array_shape); scalars carry the names of the `noahmplsm` dummy arguments.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, _lib
+
+SYNC_FULL, SYNC_RESIDENT = 0, 1
+MATH_FAST, MATH_PARITY = 0, 1
+
+# messages the reference passes to wrf_error_fatal for each status code (include/noahmp_b200.h)
+ERROR_TEXT = {
+    1: "Stop in Noah-MP (ERRSW)", 2: "Energy budget problem in NOAHMP LSM", 3: "Water budget problem in NOAHMP LSM",
+    4: "STOP in Noah-MP (emitted longwave <0)", 5: "CRITICAL PROBLEM: HCAN <= ZPD", 6: "STOP in Noah-MP (ZLVL <= ZPD)",
+    7: "REDPRM: table index out of range", 8: "unsupported option value", 100: "CUDA failure", 101: "bad argument",
+}
+
+
+class NoahmpError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__(f"noahmp_b200 error {code}: {ERROR_TEXT.get(code, '?')} {detail}".strip())
+
+
+def read_tables(directory, dataset="USGS", soil="STAS"):
+    """MPTABLE/VEGPARM/SOILPARM/GENPARM.TBL -> _capi.NoahmpTables through the library's C++ reader."""
+    t = _capi.NoahmpTables()
+    rc = _lib.lib().noahmp_b200_read_tables(str(directory).encode(), dataset.encode(), soil.encode(), C.byref(t))
+    if rc:
+        raise NoahmpError(rc, _lib.lib().noahmp_b200_tables_error().decode())
+    return t
+
+
+def proc_grid(nproc):
+    nx, ny = C.c_int(), C.c_int()
+    _lib.lib().noahmp_b200_proc_grid(nproc, C.byref(nx), C.byref(ny))
+    return nx.value, ny.value
+
+
+def tile(global_nx, global_ny, nproc, rank):
+    """(xstart, xend, ystart, yend), 1-based inclusive, of `rank` (mpp_land_partition_calc)."""
+    v = [C.c_int() for _ in range(4)]
+    _lib.lib().noahmp_b200_tile(global_nx, global_ny, nproc, rank, *[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+class _DevArray:
+    """Zero-copy view of a device plane for torch.as_tensor / cupy (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class NoahMP:
+    """One tile of ni x nj grid cells on one GPU."""
+
+    def __init__(self, tables, ni, nj, device=0, sync=SYNC_FULL, math=MATH_FAST):
+        self._L = _lib.lib()
+        if isinstance(tables, dict):
+            tables = _capi.tables_from_dict(tables)
+        self.tables = tables
+        self.ni, self.nj = ni, nj
+        self._ctx = self._L.noahmp_b200_create(device, C.byref(tables), ni, nj)
+        if not self._ctx:
+            raise NoahmpError(100, self._L.noahmp_b200_last_error().decode())
+        self.set_mode(sync)
+        self.set_math(math)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.noahmp_b200_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc in (100, 101, 8):
+            raise NoahmpError(rc, self._L.noahmp_b200_last_error().decode())
+        return rc
+
+    def set_mode(self, sync):
+        self._check(self._L.noahmp_b200_set_mode(self._ctx, sync))
+
+    def set_math(self, math):
+        self._check(self._L.noahmp_b200_set_math(self._ctx, math))
+
+    # ---- the reference-facing call -------------------------------------------------------------
+    def noahmplsm(self, arrays, scalars):
+        """CALL noahmplsm(...): updates the INOUT/OUT arrays in place (SYNC_FULL) and returns NoahmpStatus."""
+        a = _capi.make_args(arrays, scalars)
+        st = _capi.NoahmpStatus()
+        self._check(self._L.noahmp_b200_noahmplsm(self._ctx, C.byref(a), C.byref(st)))
+        return st
+
+    def sync_host(self, arrays, scalars):
+        a = _capi.make_args(arrays, scalars)
+        self._check(self._L.noahmp_b200_sync_host(self._ctx, C.byref(a)))
+
+    # ---- device-resident stepping ----------------------------------------------------------------
+    def upload(self, arrays, scalars):
+        a = _capi.make_args(arrays, scalars)
+        self._check(self._L.noahmp_b200_upload(self._ctx, C.byref(a)))
+
+    def device_forcing(self):
+        """List of 12 device planes (nj, ni) in the order documented in include/noahmp_b200.h."""
+        ptrs = (C.c_void_p * 12)()
+        self._check(self._L.noahmp_b200_device_forcing(self._ctx, ptrs))
+        return [_DevArray(p, (self.nj, self.ni)) for p in ptrs]
+
+    def bind_forcing(self, ptrs=None):
+        """ptrs: 12 device addresses (ints) of caller-owned (nj, ni) float32 planes, or None to unbind."""
+        if ptrs is None:
+            self._check(self._L.noahmp_b200_bind_forcing(self._ctx, None))
+        else:
+            arr = (C.c_void_p * 12)(*[int(p) for p in ptrs])
+            self._check(self._L.noahmp_b200_bind_forcing(self._ctx, arr))
+
+    def fetch(self, arrays, scalars, field):
+        a = _capi.make_args(arrays, scalars)
+        self._check(self._L.noahmp_b200_fetch(self._ctx, C.byref(a), field.encode()))
+
+    def step_device(self, itimestep, yr, julian, dt, stream=None):
+        self._check(self._L.noahmp_b200_step_device(self._ctx, itimestep, yr, julian, dt, stream))
+
+    def status(self):
+        st = _capi.NoahmpStatus()
+        self._check(self._L.noahmp_b200_get_status(self._ctx, C.byref(st)))
+        return st
+
+    def device_state(self, field, layer=0):
+        n = C.c_longlong()
+        p = self._L.noahmp_b200_device_state(self._ctx, field.encode(), layer, C.byref(n))
+        if not p:
+            raise KeyError(field)
+        return _DevArray(p, (n.value,), "<i4" if field in _capi.INT_ARRAYS else "<f4")
+
+    # ---- bookkeeping -------------------------------------------------------------------------------
+    @property
+    def launches(self):
+        return self._L.noahmp_b200_launch_count(self._ctx)
+
+    @property
+    def variant(self):
+        return self._L.noahmp_b200_kernel_variant(self._ctx).decode()
+
+    def census(self):
+        c = (C.c_int64 * 4)()
+        self._check(self._L.noahmp_b200_census(self._ctx, c))
+        return dict(land=c[0], glacier=c[1], seaice=c[2], water=c[3])
+
+    def column_map(self):
+        n = sum(v for k, v in self.census().items() if k != "water")
+        out = np.empty(n, np.int32)
+        self._check(self._L.noahmp_b200_column_map(self._ctx, out.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        return out
+
+    def enable_iteration_counts(self, on=True):
+        self._check(self._L.noahmp_b200_enable_iteration_counts(self._ctx, int(on)))
+
+    def iteration_counts(self):
+        out = np.empty((self.nj, self.ni), np.int32)
+        self._check(self._L.noahmp_b200_get_iteration_counts(self._ctx, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out

@@ -1,0 +1,294 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on identical
+synthetic forcing and initial state.
+
+Bars (BASELINE.json north_star):
+  * integer / index outputs (ISNOWXY, column permutation, class census): bit-exact in every mode;
+  * PARITY math build (portable transcendentals, no FMA contraction) vs the oracle's portable-math mode:
+    every word of every INOUT/OUT array bit-identical, after 1 step and after many steps;
+  * FAST math build (libdevice, FMA) vs the oracle with host libm: per-variable tolerances below, stated as
+    (abs tolerance, max fraction of columns allowed outside it) because single-ulp differences can flip the
+    model's hard thresholds (snow-layer creation, Newton exit) in isolated columns.
+"""
+import numpy as np
+import pytest
+
+from noahmp_b200 import _capi, synthetic as S
+
+from helpers import clone_state, diff_report, make_case, run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+# per-variable tolerances of the FAST build: name -> (abs tol, allowed outlier fraction)
+FAST_TOL = {
+    "tsk": (0.05, 2e-3), "tslb": (0.02, 2e-3), "smois": (2e-4, 2e-3), "sh2o": (2e-4, 2e-3),
+    "snow": (0.05, 2e-3), "snowh": (5e-4, 2e-3), "hfx": (1.0, 5e-3), "lh": (1.0, 5e-3), "grdflx": (1.0, 5e-3),
+    "sfcrunoff": (0.01, 2e-3), "udrunoff": (0.01, 2e-3), "xlaixy": (1e-3, 2e-3),
+}
+
+
+def _model(tables, cfg_or_shape, math, sync=0):
+    import noahmp_b200
+    ni, nj = cfg_or_shape
+    return noahmp_b200.NoahMP(tables, ni, nj, device=0, sync=sync, math=math)
+
+
+def _cfg(name, ni=None, nj=None, **opts):
+    cfg = S.named_config(name)
+    if ni:
+        cfg.ni, cfg.nj = ni, nj
+    cfg.opts.update(opts)
+    return cfg
+
+
+def _bitexact(cfg, tables, nsteps, check_at=(1,)):
+    import noahmp_b200
+    ts = _capi.tables_from_dict(tables)
+    _, st, state0 = make_case(cfg, tables)
+    s_cpu, s_gpu = clone_state(state0), clone_state(state0)
+    m = _model(tables, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY)
+    done = 0
+    for upto in sorted(set(check_at) | {nsteps}):
+        n = upto - done
+        e1 = run_oracle(cfg, ts, st, s_cpu, n, math_mode=1, first_step=done + 1)
+        e2 = run_gpu(m, cfg, st, s_gpu, n, first_step=done + 1)
+        done = upto
+        assert e1 == e2, (e1, e2)
+        rep = diff_report(s_cpu, s_gpu)
+        assert not rep, f"after {upto} steps: {rep}"
+    assert e1 is None, f"model conservation check failed: {e1}"
+    m.close()
+    return s_cpu
+
+
+def test_c1_bitexact_24_steps(built, tables_usgs):
+    """BASELINE config 0: 10x10, default options, 24 hourly steps."""
+    _bitexact(_cfg("C1"), tables_usgs, 24, check_at=(1, 12))
+
+
+def test_c2_bitexact_nldas(built, tables_usgs):
+    """BASELINE config 1: NLDAS 464x224 with water mask; bit-exact after 1 and 24 steps."""
+    _bitexact(_cfg("C2"), tables_usgs, 24, check_at=(1,))
+
+
+def test_c2_tile_bitexact_240_steps(built, tables_usgs):
+    """240 hourly steps (10 days) on a 116x112 NLDAS tile (the 8-rank tile size)."""
+    _bitexact(_cfg("C2", 116, 112), tables_usgs, 240, check_at=(1, 120))
+
+
+def test_c3_dynveg_snow_bitexact(built, tables_usgs):
+    """BASELINE config 2 physics (dveg=2, 3-layer snow) on a 192x160 tile, 48 steps."""
+    s = _bitexact(_cfg("C3", 192, 160), tables_usgs, 48, check_at=(1,))
+    assert (s["isnowxy"] == -3).mean() > 0.2 and (s["isnowxy"] == 0).mean() > 0.02  # all snow bins exercised
+
+
+def test_c4_glacier_water_bitexact(built, tables_usgs):
+    """BASELINE config 3 population (water mask + 10 % glacier) on a 240x180 tile, 48 steps."""
+    s = _bitexact(_cfg("C4", 240, 180), tables_usgs, 48, check_at=(1,))
+    assert np.isfinite(s["tsk"]).all()
+
+
+@pytest.mark.parametrize("opts", [
+    dict(idveg=1, iopt_crs=2, iopt_btr=2, iopt_run=2, iopt_sfc=2, iopt_frz=2, iopt_inf=2, iopt_rad=1, iopt_alb=1,
+         iopt_snf=2, iopt_tbot=1, iopt_stc=2),
+    dict(idveg=3, iopt_crs=1, iopt_btr=3, iopt_run=3, iopt_sfc=1, iopt_frz=1, iopt_inf=1, iopt_rad=2, iopt_alb=2,
+         iopt_snf=3, iopt_tbot=2, iopt_stc=1),
+    dict(idveg=5, iopt_crs=2, iopt_btr=1, iopt_run=4, iopt_sfc=2, iopt_frz=2, iopt_inf=1, iopt_rad=3, iopt_alb=1,
+         iopt_snf=1, iopt_tbot=2, iopt_stc=2),
+    dict(idveg=2, iopt_crs=1, iopt_btr=1, iopt_run=5, iopt_sfc=1, iopt_frz=1, iopt_inf=2, iopt_rad=3, iopt_alb=2,
+         iopt_snf=1, iopt_tbot=2, iopt_stc=1),
+])
+def test_option_combinations_bitexact(built, tables_usgs, opts):
+    """Every opt_* value the reference supports offline, through the run-time-option kernel."""
+    cfg = _cfg("C3", 64, 48, **opts)
+    cfg.glacier_frac = 0.1
+    import noahmp_b200
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    if opts["iopt_run"] == 5:  # state the MMF scheme needs (GROUNDWATER_INIT is a "next" row)
+        state0["smoiseq"][...] = 0.8 * state0["smois"]
+        state0["zwtxy"][...] = -3.0
+        state0["smcwtdxy"][...] = 0.3
+    s_cpu, s_gpu = clone_state(state0), clone_state(state0)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY)
+    e1 = run_oracle(cfg, ts, st, s_cpu, 12, math_mode=1)
+    e2 = run_gpu(m, cfg, st, s_gpu, 12)
+    assert m.variant == "runtime"
+    assert e1 == e2, (e1, e2)
+    skip = set()
+    if opts["iopt_sfc"] == 2:  # FH2 is read undefined by the reference there
+        skip = {"t2mvxy", "t2mbxy", "q2mvxy", "q2mbxy", "chv2xy", "chb2xy"}
+    rep = diff_report(s_cpu, s_gpu, [n for n in _capi.INOUT_NAMES + _capi.OUT_NAMES if n not in skip])
+    assert not rep, rep
+    m.close()
+
+
+def test_specialised_kernels_equal_runtime_kernel(built, tables_usgs):
+    """The opt_*-as-template instantiations ('default', 'dynveg') give the same bits as the generic kernel."""
+    import noahmp_b200
+    for name, variant in (("C2", "default"), ("C3", "dynveg")):
+        cfg = _cfg(name, 96, 80)
+        _, st, state0 = make_case(cfg, tables_usgs)
+        a, b = clone_state(state0), clone_state(state0)
+        m1 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST)
+        run_gpu(m1, cfg, st, a, 6)
+        assert m1.variant == variant
+        # same options but iz0tlnd untouched; force the runtime kernel by an option set no template matches
+        cfg2 = _cfg(name, 96, 80)
+        cfg2.opts["iopt_snf"] = 1
+        m2 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST)
+        import os
+        os.environ["NOAHMP_B200_FORCE_RUNTIME"] = "1"
+        try:
+            run_gpu(m2, cfg2, st, b, 6)
+        finally:
+            del os.environ["NOAHMP_B200_FORCE_RUNTIME"]
+        assert m2.variant == "runtime"
+        rep = diff_report(a, b)
+        assert not rep, (name, rep)
+        m1.close(); m2.close()
+
+
+def test_fast_math_within_tolerance(built, tables_usgs):
+    """Production build (libdevice + FMA) vs oracle with host libm, 24 steps on an NLDAS tile."""
+    import noahmp_b200
+    cfg = _cfg("C2", 232, 112)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    s_cpu, s_gpu = clone_state(state0), clone_state(state0)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST)
+    e1 = run_oracle(cfg, ts, st, s_cpu, 24, math_mode=0)
+    e2 = run_gpu(m, cfg, st, s_gpu, 24)
+    assert e1 is None and e2 is None, (e1, e2)  # ERRSW / ERRENG / ERRWAT under the reference thresholds
+    land = st["xland"] < 1.5
+    for name, (tol, frac) in FAST_TOL.items():
+        x, y = s_cpu[name], s_gpu[name]
+        mask = land if x.ndim == 2 else np.broadcast_to(land[:, None, :], x.shape)
+        d = np.abs(x.astype(np.float64) - y)[mask]
+        out = float((d > tol).mean())
+        assert out <= frac, f"{name}: {out:.2e} of columns differ by more than {tol} (max {d.max():.3g})"
+    assert (s_cpu["isnowxy"] != s_gpu["isnowxy"]).mean() <= 2e-3
+    m.close()
+
+
+def test_resident_mode_equals_full_sync(built, tables_usgs):
+    """State kept in HBM across steps (forcing-only upload) ends bit-identical to the strict drop-in mode."""
+    import noahmp_b200
+    cfg = _cfg("C4", 160, 120)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    a, b = clone_state(state0), clone_state(state0)
+    m1 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST, sync=noahmp_b200.SYNC_FULL)
+    m2 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST, sync=noahmp_b200.SYNC_RESIDENT)
+    run_gpu(m1, cfg, st, a, 10)
+    run_gpu(m2, cfg, st, b, 10)
+    assert diff_report(a, state0)  # FULL mode moved the host arrays
+    xp = S.backend()
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 10, st), b, 10)
+    m2.sync_host(arr, sc)
+    rep = diff_report(a, b)
+    assert not rep, rep
+    m1.close(); m2.close()
+
+
+def test_column_map_and_census_bitexact(built, tables_usgs):
+    """Partition maps / column permutation: land | glacier | sea-ice, each in grid order (bit-exact contract)."""
+    import noahmp_b200
+    cfg = _cfg("C4", 200, 150)
+    _, st, state = make_case(cfg, tables_usgs)
+    st["xice"][5:9, 7:30] = 1.0  # some sea-ice cells
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST)
+    xp = S.backend()
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), state, 1)
+    m.upload(arr, sc)
+    water = (st["xland"] - np.float32(1.5)) >= 0
+    seaice = ~water & (st["xice"] >= np.float32(sc["xice_thres"]))
+    glac = ~water & ~seaice & (st["ivgtyp"] == sc["isice"])
+    land = ~water & ~seaice & ~glac
+    want = np.concatenate([np.flatnonzero(land.ravel()), np.flatnonzero(glac.ravel()),
+                           np.flatnonzero(seaice.ravel())]).astype(np.int32)
+    assert m.census() == dict(land=int(land.sum()), glacier=int(glac.sum()), seaice=int(seaice.sum()),
+                              water=int(water.sum()))
+    assert np.array_equal(m.column_map(), want)
+    m.close()
+
+
+def test_seaice_water_and_first_step_rules(built, tables_usgs):
+    """Open-water cells untouched except the ITIMESTEP==1 fill; sea-ice cells get SH2O=1, XLAI=0.01 only."""
+    import noahmp_b200
+    cfg = _cfg("C4", 96, 64)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    st["xice"][10:14, 3:40] = 1.0
+    s_cpu, s_gpu = clone_state(state0), clone_state(state0)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY)
+    run_oracle(cfg, ts, st, s_cpu, 2, math_mode=1)
+    run_gpu(m, cfg, st, s_gpu, 2)
+    assert not diff_report(s_cpu, s_gpu)
+    water = st["xland"] >= 1.5
+    assert (s_gpu["smois"][np.broadcast_to(water[:, None, :], s_gpu["smois"].shape)] == 1.0).all()
+    assert (s_gpu["tsk"][water] == state0["tsk"][water]).all()
+    m.close()
+
+
+def test_error_status_matches_oracle(built, tables_usgs):
+    """A REDPRM range violation is reported with the reference's first-failing (i,j) and the count."""
+    import noahmp_b200
+    cfg = _cfg("C1", 12, 9)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    st["isltyp"][4, 7] = 25  # > SLCATS
+    st["isltyp"][6, 2] = 0
+    s_cpu, s_gpu = clone_state(state0), clone_state(state0)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY)
+    e1 = run_oracle(cfg, ts, st, s_cpu, 1, math_mode=1)
+    e2 = run_gpu(m, cfg, st, s_gpu, 1)
+    assert e1 is not None and e1 == e2, (e1, e2)
+    assert e1[1] == 7 and (e1[2], e1[3]) == (8, 5) and e1[4] == 2
+    assert not diff_report(s_cpu, s_gpu)
+    m.close()
+
+
+def test_full_size_properties_conus(built, tables_usgs):
+    """BASELINE full size (CONUS 4608x3840 is tiled 8-ways as 1152x1920): size-independent properties on one
+    such tile — tiling invariance (a sub-tile run alone gives the bits the big tile gives there), the model's
+    own conservation checks, and invariants of the snow/soil state."""
+    import noahmp_b200
+    cfg = S.named_config("C3")
+    xs, xe, ys, ye = noahmp_b200.tile(cfg.ni, cfg.nj, 8, 5)
+    assert (xe - xs + 1, ye - ys + 1) == (1152, 1920)
+    ni, nj = xe - xs + 1, ye - ys + 1
+    xp = S.backend()
+    st = S.static_fields(xp, cfg, xs, xe, ys, ye)
+    state = S.cold_start(cfg, st, S.forcing(xp, cfg, 1, st), tables_usgs)
+    big = clone_state(state)
+    m = _model(tables_usgs, (ni, nj), noahmp_b200.MATH_PARITY)
+    err = None
+    for step in (1, 2, 3):
+        arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, step, st), big, step)
+        sc.update(ims=xs, ime=xe, its=xs, ite=xe, jms=ys, jme=ye, jts=ys, jte=ye, ide=cfg.ni, jde=cfg.nj)
+        s = m.noahmplsm(arr, sc)
+        err = err or (s.code and (step, s.code, s.i, s.j, s.value))
+    m.close()
+    assert not err, err
+    # invariants
+    isn = big["isnowxy"]
+    assert isn.min() >= -3 and isn.max() <= 0
+    z = big["zsnsoxy"]
+    for k in range(7):
+        active = (k - 2) > isn
+        assert (z[:, k, :][active] < 0).all()
+        if k:
+            both = active & ((k - 3) > isn)
+            assert (z[:, k, :][both] < z[:, k - 1, :][both]).all()  # strictly deeper
+    assert (big["snicexy"][np.broadcast_to((np.arange(3)[None, :, None] - 2) <= isn[:, None, :],
+                                           big["snicexy"].shape)] == 0).all()
+    assert ((big["sh2o"] <= big["smois"] + 1e-6) & (big["smois"] > 0)).all()
+    # tiling invariance against the oracle on a 64x48 window of the same tile
+    wx, wy = 300, 1000
+    sub = dict(xs=xs + wx, xe=xs + wx + 63, ys=ys + wy, ye=ys + wy + 47)
+    st2 = S.static_fields(xp, cfg, sub["xs"], sub["xe"], sub["ys"], sub["ye"])
+    small = S.cold_start(cfg, st2, S.forcing(xp, cfg, 1, st2), tables_usgs)
+    ts = _capi.tables_from_dict(tables_usgs)
+    run_oracle(cfg, ts, st2, small, 3, math_mode=1)
+    for n in ("tsk", "snow", "isnowxy", "hfx", "lh", "xlaixy"):
+        assert np.array_equal(small[n], big[n][wy:wy + 48, wx:wx + 64]), n
+    assert np.array_equal(small["tslb"], big["tslb"][wy:wy + 48, :, wx:wx + 64])
