@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
     ap.add_argument("--grid", type=int, nargs=2, default=None, help="override ni nj (testing only)")
-    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[768, 640, 12], help="ni nj steps of the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[1536, 1280, 16], help="ni nj steps of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--math", default="fast", choices=["fast", "parity"])
@@ -226,7 +226,7 @@ def main():
         planes["dz8w"] = torch.full((nj, ni), 60.0, device=dev)
         ring.append([planes[k] for k in FORCING_ORDER])
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # the physics kernels are launched on this stream and timed on it
 
     def device_step(k):  # k = 0-based global step counter
         yr, julian, _ = S.clock(cfg, 1 + k)

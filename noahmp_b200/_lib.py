@@ -11,7 +11,7 @@ import subprocess
 from . import _capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnoahmp_b200.so")
+SO_PATH = os.environ.get("NOAHMP_B200_LIB") or os.path.join(_HERE, "libnoahmp_b200.so")
 _LIB = None
 
 _pa = C.POINTER(_capi.NoahmpLsmArgs)

@@ -17,6 +17,26 @@
 #ifndef NMP_PARITY
 #define NMP_PARITY 0
 #endif
+#ifndef NMP_FASTMATH
+#define NMP_FASTMATH 0
+#endif
+// Threads per block of the physics kernels and the phase barrier: with NMP_PHASE_SYNC the warps of a block
+// walk through the (several hundred KB of) straight-line physics code in step, so an instruction-cache line
+// fetched from L2 by the first warp is reused by the others (DESIGN.md "instruction fetch").
+#ifndef NMP_BLOCK
+#define NMP_BLOCK 128
+#endif
+#ifndef NMP_MINBLOCKS
+#define NMP_MINBLOCKS 1
+#endif
+#ifndef NMP_PHASE_SYNC
+#define NMP_PHASE_SYNC 0
+#endif
+#if NMP_PHASE_SYNC
+#define NMP_PHASE() __syncthreads()
+#else
+#define NMP_PHASE() ((void)0)
+#endif
 
 #define NMP_DEV __device__ __forceinline__
 #define NMP_DEVN __device__ __noinline__
@@ -45,6 +65,23 @@ NMP_DEV float ACOS(float x) { return nmpm::acosf_(x); }
 NMP_DEV float TANH(float x) { return nmpm::tanhf_(x); }
 NMP_DEV float SQRT(float x) { return __fsqrt_rn(x); }
 NMP_DEV float DIV(float a, float b) { return __fdiv_rn(a, b); }
+#elif NMP_FASTMATH
+// Production arithmetic: SFU-based exp2/log2 (MUFU.EX2 / MUFU.LG2) instead of the ~100-instruction libdevice
+// powf/expf/logf expansions; relative error <= ~1e-6 over the ranges the physics uses (|y*log2 x| < 60).
+// The translation unit is compiled with -prec-div=false -prec-sqrt=false as well.  Rarely used functions
+// (opt_rad=1 geometry, TANH of the snow-cover fraction, ATAN of the unstable profile) stay on libdevice.
+NMP_DEV float EXP(float x) { return __expf(x); }
+NMP_DEV float LOG(float x) { return __logf(x); }
+NMP_DEV float LOG10(float x) { return __log10f(x); }
+NMP_DEV float POW(float x, float y) { return __powf(x, y); }
+NMP_DEV double DPOW(double x, double y) { return pow(x, y); }
+NMP_DEV float ATAN(float x) { return atanf(x); }
+NMP_DEV float TAN(float x) { return tanf(x); }
+NMP_DEV float COS(float x) { return cosf(x); }
+NMP_DEV float ACOS(float x) { return acosf(x); }
+NMP_DEV float TANH(float x) { return tanhf(x); }
+NMP_DEV float SQRT(float x) { return sqrtf(x); }
+NMP_DEV float DIV(float a, float b) { return a / b; }
 #else
 NMP_DEV float EXP(float x) { return expf(x); }
 NMP_DEV float LOG(float x) { return logf(x); }

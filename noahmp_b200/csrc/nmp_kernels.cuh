@@ -218,9 +218,12 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const StepParams& p) {
 
 // ---- land columns: REDPRM + NOAHMP_SFLX (noahmpdrv.F90:449-547, :681-714) ---------------------------
 template <class O>
-__global__ void __launch_bounds__(128) land_kernel(const __grid_constant__ StepParams p) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.count) return;
+__global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __grid_constant__ StepParams p) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // threads past the end redo the last column and skip the stores, so that every thread of the block reaches
+  // the phase barriers inside NOAHMP_SFLX
+  const bool live = t < p.count;
+  if (!live) t = p.count - 1;
   const ColumnIO io(p, (long long)p.first + t);
   Ctx c;
   init_ctx(c, p);
@@ -266,9 +269,16 @@ __global__ void __launch_bounds__(128) land_kernel(const __grid_constant__ StepP
   s.VEGTYP = VEGTYP;
   s.URBAN = (VEGTYP == p.isurban);
 
-  if (REDPRM(c, VEGTYP, SOILTYP, 1, s.URBAN)) {
-    report_error(p, io.cell, c.err, c.errv);
-    return;
+  const bool bad_index = REDPRM(c, VEGTYP, SOILTYP, 1, s.URBAN) != 0;
+  if (bad_index) {
+    // REDPRM range violation: the column is reported and left untouched; it still walks through the physics with
+    // a valid parameter row so that the block's barriers stay matched
+    Ctx c2;
+    init_ctx(c2, p);
+    REDPRM(c2, 19, 1, 1, false);
+    c.P = c2.P;
+    s.VEGTYP = 19;
+    s.URBAN = false;
   }
   // every OUT member is assigned by NOAHMP_SFLX before use except on the dveg error path
   s.PONDING = 0.f; s.PONDING1 = 0.f; s.PONDING2 = 0.f; s.QSNBOT = 0.f; s.FPICE = 0.f;
@@ -287,9 +297,11 @@ __global__ void __launch_bounds__(128) land_kernel(const __grid_constant__ StepP
   o.EVG = s.EVG; o.GHV = s.GHV; o.IRB = s.IRB; o.SHB = s.SHB; o.EVB = s.EVB; o.GHB = s.GHB; o.TR = s.TR;
   o.EVC = s.EVC; o.CHLEAF = s.CHLEAF; o.CHUC = s.CHUC; o.CHV2 = s.CHV2; o.CHB2 = s.CHB2; o.FSNO = s.FSNO;
   o.RECH = s.RECH; o.DEEPRECH = s.DEEPRECH; o.SMCWTD = s.SMCWTD;
-  store_column(io, p, s, o);
-  if (p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
-  if (c.err) report_error(p, io.cell, c.err, c.errv);
+  if (live && !bad_index) {
+    store_column(io, p, s, o);
+    if (p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
+  }
+  if (live && c.err) report_error(p, io.cell, c.err, c.errv);
 }
 
 // ---- glacier columns: NOAHMP_GLACIER + sentinel fills (noahmpdrv.F90:552-628) ------------------------
@@ -344,7 +356,7 @@ void launch_pair(const StepParams& base, int nland, int nglac, cudaStream_t stre
     StepParams p = base;
     p.first = 0;
     p.count = nland;
-    land_kernel<O><<<(nland + 127) / 128, 128, 0, stream>>>(p);
+    land_kernel<O><<<(nland + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
     ++*launches;
   }
   if (nglac > 0) {
@@ -372,6 +384,10 @@ bool matches(const int* opt) {
 // Picks the specialised instantiation when the namelist options match one, else the generic kernel that
 // reads the options at run time.  Returns the name of the variant (for logs / tests).
 const char* launch_step(const StepParams& base, int nland, int nglac, cudaStream_t stream, long long* launches) {
+#ifdef NMP_ONLY_DYNVEG
+  launch_pair<OptDynVeg>(base, nland, nglac, stream, launches);
+  return "dynveg";
+#endif
 #ifndef NMP_NO_SPECIALISE
   if (getenv("NOAHMP_B200_FORCE_RUNTIME")) {
     launch_pair<OptRuntime>(base, nland, nglac, stream, launches);

@@ -2,7 +2,6 @@
 // compiled with -fmad=false so that every fp32 operation rounds exactly as in the CPU oracle (g++
 // -ffp-contract=off).  Only the run-time-option instantiation is built here.
 #define NMP_PARITY 1
-#define NMP_NO_SPECIALISE 1
 #include "nmp_kernels.cuh"
 
 const char* nmp_launch_step_parity(const nmpf::StepParams& base, int nland, int nglac, cudaStream_t stream,

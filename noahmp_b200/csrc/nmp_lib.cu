@@ -138,8 +138,8 @@ __global__ void scatter_kernel(const PlaneDesc* __restrict__ planes, const int* 
   d.grid[(long long)i + (long long)d.layer * ni + (long long)j * ni * d.layers] = state[(long long)d.plane * np + n];
 }
 
-// ITIMESTEP == 1 initialisation of open-water and full sea-ice cells (noahmpdrv.F90:399-419); works on the
-// grid-order staging arrays because those cells have no compact column.
+// ITIMESTEP == 1 initialisation of open-water cells (noahmpdrv.F90:399-411); works on the grid-order staging
+// arrays because those cells have no compact column (the XICE == 1 branch lives in seaice_kernel).
 __global__ void first_step_water_kernel(const float* __restrict__ xland, const float* __restrict__ xice, float* smstav,
                                         float* smstot, float* smois, float* tslb, int ni, long long ncell) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,25 +153,30 @@ __global__ void first_step_water_kernel(const float* __restrict__ xland, const f
       smois[i + (long long)k * ni + j * ni * NOAHMP_NSOIL] = 1.0f;
       tslb[i + (long long)k * ni + j * ni * NOAHMP_NSOIL] = 273.16f;
     }
-  } else if (xice[c] == 1.f) {
-    smstav[c] = 1.0f;
-    smstot[c] = 1.0f;
-    for (int k = 0; k < NOAHMP_NSOIL; ++k) smois[i + (long long)k * ni + j * ni * NOAHMP_NSOIL] = 1.0f;
   }
 }
 
-// sea-ice columns: SH2O = 1, XLAI = 0.01 (noahmpdrv.F90:436-441)
-__global__ void seaice_kernel(float* state, long long np, int first, int count) {
+// sea-ice columns: SH2O = 1, XLAI = 0.01 (noahmpdrv.F90:436-441); at ITIMESTEP == 1 the row initialisation
+// (:412-418) also sets SMSTAV = SMSTOT = SMOIS = 1 where XICE == 1
+__global__ void seaice_kernel(float* state, const int* __restrict__ cell, const float* __restrict__ xice, long long np,
+                              int first, int count, int itimestep) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   long long n = (long long)first + t;
+  if (itimestep == 1 && xice[cell[n]] == 1.f) {
+    state[(long long)NMP_SLOT(smstav) * np + n] = 1.0f;
+    state[(long long)NMP_SLOT(smstot) * np + n] = 1.0f;
+    for (int k = 0; k < NOAHMP_NSOIL; ++k) state[(long long)(NMP_SLOT(smois) + k) * np + n] = 1.0f;
+  }
   for (int k = 0; k < NOAHMP_NSOIL; ++k) state[(long long)(NMP_SLOT(sh2o) + k) * np + n] = 1.0f;
   state[(long long)NMP_SLOT(xlaixy) * np + n] = 0.01f;
 }
 
 // ---- helpers ------------------------------------------------------------------------------------------
 static void pin(noahmp_b200_ctx* ctx, const void* p, size_t bytes) {
-  if (!ctx->pin_host || !p || !bytes) return;
+  // Only large arrays are page-locked: they come from mmap'ed allocations of their own, whereas small heap
+  // arrays can share a page with other data, and a partially registered range makes cudaMemcpyAsync fail.
+  if (!ctx->pin_host || !p || bytes < (size_t)(4u << 20)) return;
   auto it = ctx->registered.find(p);
   if (it != ctx->registered.end() && it->second >= bytes) return;
   if (it != ctx->registered.end()) cudaHostUnregister(const_cast<void*>(p));
@@ -566,7 +571,7 @@ int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float j
   p.dt = dt;
   CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), s));
   CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), s));
-  if (itimestep == 1 && ctx->nclass[CL_WATER] + ctx->nclass[CL_SEAICE] > 0) {
+  if (itimestep == 1 && ctx->nclass[CL_WATER] > 0) {
     const int T = 256;
     first_step_water_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, s>>>(
         ctx->d_stat[ST_XLAND], ctx->d_stat[ST_XICE], ctx->d_grid[F_smstav], ctx->d_grid[F_smstot],
@@ -578,7 +583,8 @@ int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float j
                                                        : nmp_launch_step_fast(p, nland, nglac, s, &ctx->launches);
   ctx->variant = v;
   if (nsea > 0) {
-    seaice_kernel<<<(nsea + 255) / 256, 256, 0, s>>>(ctx->d_state, ctx->np, nland + nglac, nsea);
+    seaice_kernel<<<(nsea + 255) / 256, 256, 0, s>>>(ctx->d_state, ctx->d_cell, ctx->d_stat[ST_XICE], ctx->np, nland + nglac,
+                                                     nsea, itimestep);
     ctx->launches++;
   }
   CK(cudaGetLastError());

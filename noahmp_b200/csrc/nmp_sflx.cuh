@@ -193,15 +193,18 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
 
   float CWP = tv1(T.cwpvt, s.VEGTYP);
 
+  NMP_PHASE();
   N3 SNICEV, SNLIQV, EPORE;
   THERMOPROP(c, s.ISNOW, IST, L.DZSNSO, s.DT, s.SNOWH, s.SNICE, s.SNLIQ, P.CSOIL, s.SMC, s.SH2O, s.STC, s.URBAN, DF,
              HCPCT, SNICEV, SNLIQV, EPORE, FACT);
 
+  NMP_PHASE();
   RadOut r;
   RADIATION<O>(c, s.VEGTYP, IST, ISC, s.SNEQVO, s.SNEQV, s.DT, s.COSZ, s.TG, s.TV, s.FSNO, s.QSNOW, s.FWET, L.ELAI,
                L.ESAI, s.SMC(1), L.SOLAD, L.SOLAI, s.FVEG, s.ALBOLD, s.TAUSS, r);
   s.SAV = r.SAV; s.SAG = r.SAG; s.FSR = r.FSR; s.FSA = r.FSA; s.BGAP = r.BGAP; s.WGAP = r.WGAP;
 
+  NMP_PHASE();
   float EMV = 1.f - EXP(-(L.ELAI + L.ESAI) / 1.0f);
   float EMG;
   if (s.ICE == 1) EMG = 0.98f * (1.f - s.FSNO) + 1.0f * s.FSNO;
@@ -254,6 +257,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
   else { L.LATHEAG = HSUB; L.FROZEN_GROUND = true; }
   float GAMMAG = CPAIR * s.SFCPRS / (0.622f * L.LATHEAG);
 
+  NMP_PHASE();
   FluxIn in;
   in.ISNOW = s.ISNOW; in.VEGTYP = s.VEGTYP; in.DT = s.DT; in.SAV = s.SAV; in.SAG = s.SAG; in.LWDN = s.LWDN;
   in.UR = UR; in.UU = s.UU; in.VV = s.VV; in.SFCTMP = s.SFCTMP; in.THAIR = L.THAIR; in.QAIR = L.QAIR;
@@ -277,6 +281,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
     PSNSHA = vo.PSNSHA; s.Q2V = vo.Q2V; s.CHV2 = vo.CAH2; s.CHLEAF = vo.CHLEAF; s.CHUC = vo.CHUC;
   }
 
+  NMP_PHASE();
   s.TGB = s.TG;
   CMB = s.CM;
   s.CHB = s.CH;
@@ -286,6 +291,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
   s.CHB2 = bo.EHB2;
   (void)TAUXV; (void)TAUYV;
 
+  NMP_PHASE();
   if (VEGTILE) {
     s.FIRA = s.FVEG * s.IRG + (1.0f - s.FVEG) * s.IRB + s.IRC;
     s.FSH = s.FVEG * s.SHG + (1.0f - s.FVEG) * s.SHB + s.SHC;
@@ -320,6 +326,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
   s.APAR = r.PARSUN * r.LAISUN + r.PARSHA * r.LAISHA;
   s.PSN = PSNSUN * r.LAISUN + PSNSHA * r.LAISHA;
 
+  NMP_PHASE();
   TSNOSOI<O>(c, s.ISNOW, s.TBOT, s.ZSNSO, s.SSOIL, DF, HCPCT, P.ZBOT, s.DT, s.SNOWH, s.STC);
 
   if (NMP_OPT(stc) == 2) {
@@ -331,6 +338,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
     }
   }
 
+  NMP_PHASE();
   PHASECHANGE<O>(c, s.ISNOW, s.DT, FACT, L.DZSNSO, IST, s.STC, s.SNICE, s.SNLIQ, s.SNEQV, s.SNOWH, s.SMC, s.SH2O,
                  L.QMELT, L.IMELT, s.PONDING);
 }
@@ -352,6 +360,7 @@ NMP_DEV void WATER(Ctx& c, Col& s, SflxLocal& L) {
   s.ECAN = co.ECAN; s.ETRAN = co.ETRAN; s.QSNOW = co.QSNOW; s.FPICE = co.FPICE;
   const float QRAIN = co.QRAIN, SNOWHIN = co.SNOWHIN;
 
+  NMP_PHASE();
   QSNSUB = 0.f;
   if (s.SNEQV > 0.f) QSNSUB = MIN(L.QVAP, s.SNEQV / s.DT);
   QSEVA = L.QVAP - QSNSUB;
@@ -363,6 +372,7 @@ NMP_DEV void WATER(Ctx& c, Col& s, SflxLocal& L) {
             s.SNEQV, s.SNICE, s.SNLIQ, s.SH2O(1), L.SICE(1), s.STC, s.ZSNSO, L.DZSNSO, s.QSNBOT, SNOFLOW, s.PONDING1,
             s.PONDING2);
 
+  NMP_PHASE();
   if (L.FROZEN_GROUND) {
     L.SICE(1) = L.SICE(1) + (QSDEW - QSEVA) * s.DT / (L.DZSNSO(1) * 1000.f);
     QSDEW = 0.0f;
@@ -381,8 +391,10 @@ NMP_DEV void WATER(Ctx& c, Col& s, SflxLocal& L) {
   for (int IZ = 1; IZ <= NSOIL; ++IZ)
     if (IZ <= P.NROOT) ETRANI(IZ) = s.ETRAN * L.BTRANI(IZ) * 0.001f;
 
+  NMP_PHASE();
   SOILWATER<O>(c, s.DT, s.ZSOIL, L.DZSNSO, QINSUR, QSEVA, ETRANI, L.SICE, s.SH2O, s.SMC, s.ZWT, s.URBAN, s.SMCWTD,
                s.DEEPRECH, s.RUNSRF, QDRAIN, s.RUNSUB, WCND, FCRMAX);
+  NMP_PHASE();
   if (run == 1) {
     float QIN, QDIS;
     GROUNDWATER(P, s.DT, L.SICE, s.ZSOIL, WCND, FCRMAX, s.SH2O, s.ZWT, s.WA, s.WT, QIN, QDIS);
@@ -444,6 +456,7 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
   if (s.URBAN || s.VEGTYP == T.isbarren) s.FVEG = 0.0f;
   if (L.ELAI + L.ESAI == 0.0f) s.FVEG = 0.0f;
 
+  NMP_PHASE();
   ENERGY<O>(c, s, L);
 
 #pragma unroll
@@ -454,8 +467,10 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
   L.QDEW = ABS(MIN(s.FGEV / L.LATHEAG, 0.f));
   s.EDIR = L.QVAP - L.QDEW;
 
+  NMP_PHASE();
   WATER<O>(c, s, L);
 
+  NMP_PHASE();
   if (dveg == 2 || dveg == 5) {
     CarbonState cs;
     cs.LFMASS = s.LFMASS; cs.RTMASS = s.RTMASS; cs.STMASS = s.STMASS; cs.WOOD = s.WOOD; cs.STBLCP = s.STBLCP;
@@ -465,6 +480,7 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
     s.FASTCP = cs.FASTCP; s.LAI = cs.LAI; s.SAI = cs.SAI; s.GPP = cs.GPP; s.NPP = cs.NPP; s.NEE = cs.NEE;
   }
 
+  NMP_PHASE();
   // ERROR (:1106-1228)
   s.ERRSW = L.SWDOWN - (s.FSA + s.FSR);
   if (ABS(s.ERRSW) > 0.01f) c.fatal(NOAHMP_ERR_ERRSW, s.ERRSW);
