@@ -353,6 +353,19 @@ float nmo_math1(int fn, float x, float y) {
     default: return 0.f;
   }
 }
+// ROSR12 probe: n unknowns (n <= 7) placed on layers NSOIL-n+1..NSOIL of the (-2:4) work arrays
+void nmo_rosr12(int n, const float* a, const float* b, const float* c, const float* d, float* x) {
+  using namespace nmo;
+  ASnSo P, A, B, C, D, DELTA;
+  P.fill(0.f); A.fill(0.f); B.fill(0.f); C.fill(0.f); D.fill(0.f); DELTA.fill(0.f);
+  const int top = NSOIL - n + 1;
+  for (int k = 0; k < n; ++k) { A(top + k) = a[k]; B(top + k) = b[k]; C(top + k) = c[k]; D(top + k) = d[k]; }
+  ROSR12(P, A, B, C, D, DELTA, top, NSOIL, NSNOW);
+  for (int k = 0; k < n; ++k) x[k] = P(top + k);
+}
+// COMBO probe: v = {DZ, WLIQ, WICE, T} of layer 1 (updated), w = the same of layer 2
+void nmo_combo(float* v, const float* w) { nmo::COMBO(v[0], v[1], v[2], v[3], w[0], w[1], w[2], w[3]); }
+
 void nmo_math_array(int fn, const float* x, const float* y, float* out, long n) {
   for (long i = 0; i < n; ++i) out[i] = nmo_math1(fn, x[i], y ? y[i] : 0.f);
 }

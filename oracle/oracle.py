@@ -35,6 +35,8 @@ def lib():
         _LIB.nmo_math1.restype = C.c_float
         _LIB.nmo_math_array.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         _LIB.nmo_esat.argtypes = [C.c_float, C.POINTER(C.c_float)]
+        _LIB.nmo_rosr12.argtypes = [C.c_int] + [C.c_void_p] * 5
+        _LIB.nmo_combo.argtypes = [C.c_void_p, C.c_void_p]
     return _LIB
 
 

@@ -1,0 +1,148 @@
+"""The CPU oracle against everything that can pin it without the reference binary: analytic known
+answers, the model's own conservation checks on every synthetic configuration, and the portable math it shares
+with the GPU parity build.  The reference ships no golden vectors for this path: PARITY UNPINNED (oracle/nmo.h)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from noahmp_b200 import _capi, synthetic as S
+
+from helpers import clone_state, diff_report, make_case, run_oracle
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+def test_esat_known_answer(O):
+    """ESAT at 0 C: the constant terms of the polynomials (noahmplsm.F90:5296-5314) -> 610.78 / 610.92 Pa."""
+    out = (C.c_float * 4)()
+    O.lib().nmo_esat(0.0, out)
+    assert abs(out[0] - 610.7799961) < 1e-3 and abs(out[1] - 610.9177956) < 1e-3
+    assert abs(out[2] - 44.38099984) < 1e-4 and abs(out[3] - 50.30305237) < 1e-4
+    O.lib().nmo_esat(20.0, out)  # 20 C over water: 2338-2340 Pa in every standard table
+    assert 2330.0 < out[0] < 2345.0
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7])
+def test_rosr12_matches_dense_solve(O, n):
+    """ROSR12 (noahmplsm.F90:5979-6036) against numpy's dense solver on diagonally dominant systems."""
+    rng = np.random.default_rng(n)
+    for _ in range(20):
+        a = rng.uniform(-1, 0, n).astype(np.float32); c = rng.uniform(-1, 0, n).astype(np.float32)
+        a[0] = 0; c[-1] = 0
+        b = (1 + np.abs(a) + np.abs(c) + rng.uniform(0, 1, n)).astype(np.float32)
+        d = rng.uniform(-5, 5, n).astype(np.float32)
+        x = np.zeros(n, np.float32)
+        O.lib().nmo_rosr12(n, a.ctypes.data, b.ctypes.data, c.ctypes.data, d.ctypes.data, x.ctypes.data)
+        M = np.diag(b.astype(np.float64)) + np.diag(a[1:].astype(np.float64), -1) + np.diag(c[:-1].astype(np.float64), 1)
+        assert np.allclose(x, np.linalg.solve(M, d.astype(np.float64)), rtol=2e-5, atol=2e-5)
+
+
+def test_combo_conserves_mass_and_follows_enthalpy_rule(O):
+    """COMBO (noahmplsm.F90:7375-7424): layer thickness, liquid and ice add; the merged temperature follows the
+    reference's three-branch enthalpy rule (HC < 0: sensible heat only; 0 <= HC <= HFUS*WLIQ: TFRZ; else warm)."""
+    CICE, CWAT, HFUS, TFRZ = 2.094e6, 4.188e6, 0.3336e6, 273.16
+    rng = np.random.default_rng(0)
+    seen = set()
+    for _ in range(400):
+        v = np.array([rng.uniform(.01, .3), rng.uniform(0, 8), rng.uniform(0.1, 60), 273.16 - 10 ** rng.uniform(-4, 1)], np.float32)
+        w = np.array([rng.uniform(.01, .3), rng.uniform(0, 8), rng.uniform(0.1, 60), 273.16 - 10 ** rng.uniform(-4, 1)], np.float32)
+        h = lambda q: (CICE * q[2] + CWAT * q[1]) * (q[3] - TFRZ) + HFUS * q[1]
+        hc = h(v.astype(np.float64)) + h(w.astype(np.float64))
+        m0 = v[:3].astype(np.float64) + w[:3]
+        O.lib().nmo_combo(v.ctypes.data, w.ctypes.data)
+        assert np.allclose(v[:3], m0, rtol=1e-6)
+        cap = CICE * m0[2] + CWAT * m0[1]
+        if hc < 0:
+            want = TFRZ + hc / cap; seen.add("cold")
+        elif hc <= HFUS * m0[1]:
+            want = TFRZ; seen.add("mixed")
+        else:
+            want = TFRZ + (hc - HFUS * m0[1]) / cap; seen.add("warm")
+        assert abs(v[3] - want) < 2e-3, (v[3], want)
+    assert {"cold", "mixed"} <= seen
+
+
+FN = dict(exp=0, log=1, log10=2, pow=3, atan=4, tan=5, cos=6, acos=7, tanh=8)
+
+
+@pytest.mark.parametrize("name,lo,hi", [("exp", -80, 80), ("log", 1e-30, 1e30), ("log10", 1e-30, 1e30), ("atan", -50, 50),
+                                        ("tanh", -12, 12), ("cos", -6.3, 6.3), ("acos", -1, 1), ("tan", -1.5, 1.5)])
+def test_portable_math_within_two_ulp_of_libm(O, name, lo, hi):
+    """csrc/nmp_math.h (what the GPU parity build and the oracle's M1 mode evaluate) vs glibc."""
+    rng = np.random.default_rng(1)
+    if lo > 0:
+        x = np.exp(rng.uniform(np.log(lo), np.log(hi), 200000)).astype(np.float32)
+    else:
+        x = rng.uniform(lo, hi, 200000).astype(np.float32)
+    O.set_math_mode(1); a = O.math_array(FN[name], x)
+    O.set_math_mode(0); b = O.math_array(FN[name], x)
+    ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+    ok = np.isfinite(b)
+    # glibc's own log10f / tanf are 2-ulp functions; the portable versions are the correctly rounded value
+    assert ulp[ok].max() <= 2, (name, int(ulp[ok].max()))
+    assert (ulp[ok] > 1).mean() < 1e-3 and (ulp[ok] > 0).mean() < 0.25
+
+
+def test_portable_pow_within_one_ulp_of_libm(O):
+    rng = np.random.default_rng(2)
+    x = np.exp(rng.uniform(np.log(1e-6), np.log(1e4), 300000)).astype(np.float32)
+    y = rng.uniform(-12, 30, 300000).astype(np.float32)
+    O.set_math_mode(1); a = O.math_array(FN["pow"], x, y)
+    O.set_math_mode(0); b = O.math_array(FN["pow"], x, y)
+    ok = np.isfinite(b) & (b > 1e-37)
+    ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+    assert ulp[ok].max() <= 1
+
+
+def _cfg(name, ni, nj):
+    cfg = S.named_config(name); cfg.ni, cfg.nj = ni, nj
+    return cfg
+
+
+@pytest.mark.parametrize("name,ni,nj,steps", [("C1", 10, 10, 24), ("C2", 116, 56, 72), ("C3", 96, 64, 48), ("C4", 120, 90, 48)])
+@pytest.mark.parametrize("math_mode", [0, 1])
+def test_conservation_checks_hold(O, tables_usgs, name, ni, nj, steps, math_mode):
+    """ERRSW / ERRENG / ERRWAT (noahmplsm.F90:1164-1226, glacier.F90:2932-2970) stay under the reference's fatal
+    thresholds on every column-step of every synthetic configuration, and the state stays finite."""
+    cfg = _cfg(name, ni, nj)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state = make_case(cfg, tables_usgs)
+    err = run_oracle(cfg, ts, st, state, steps, math_mode=math_mode, nthreads=4)
+    assert err is None, err
+    for n in ("tsk", "tslb", "smois", "sh2o", "snow", "snowh", "hfx", "lh", "xlaixy"):
+        assert np.isfinite(state[n]).all(), n
+    land = st["xland"] < 1.5
+    assert 200 < state["tsk"][land].min() and state["tsk"][land].max() < 340
+
+
+def test_oracle_thread_count_invariance(O, tables_usgs):
+    """Columns are independent: 1 thread and 5 threads give identical bits."""
+    cfg = _cfg("C4", 64, 40)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, s0 = make_case(cfg, tables_usgs)
+    a, b = clone_state(s0), clone_state(s0)
+    run_oracle(cfg, ts, st, a, 4, nthreads=1)
+    run_oracle(cfg, ts, st, b, 4, nthreads=5)
+    assert not diff_report(a, b)
+
+
+def test_math_mode_sensitivity_defines_tolerances(O, tables_usgs):
+    """oracle(host libm) vs oracle(portable math) — two <=1 ulp libms — already differ
+    by this much after 24 steps; the FAST-build tolerances of tests/test_parity_gpu.py sit above these numbers."""
+    cfg = _cfg("C2", 116, 112)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, s0 = make_case(cfg, tables_usgs)
+    a, b = clone_state(s0), clone_state(s0)
+    run_oracle(cfg, ts, st, a, 24, math_mode=0)
+    run_oracle(cfg, ts, st, b, 24, math_mode=1)
+    land = st["xland"] < 1.5
+    d = np.abs(a["tsk"] - b["tsk"])[land]
+    assert np.quantile(d, 0.999) < 0.05          # branch flips are rare ...
+    assert (a["isnowxy"] != b["isnowxy"]).mean() < 2e-3
+    assert np.abs(a["smois"] - b["smois"]).max() < 5e-3
