@@ -32,10 +32,16 @@
 #ifndef NMP_PHASE_SYNC
 #define NMP_PHASE_SYNC 0
 #endif
-#if NMP_PHASE_SYNC
+// NMP_PHASE_SYNC: 0 = no barriers, 1 = barriers between all ~16 phases, 2 = only between the major phases
+#if NMP_PHASE_SYNC == 1
 #define NMP_PHASE() __syncthreads()
+#define NMP_PHASE_MAJOR() __syncthreads()
+#elif NMP_PHASE_SYNC == 2
+#define NMP_PHASE() ((void)0)
+#define NMP_PHASE_MAJOR() __syncthreads()
 #else
 #define NMP_PHASE() ((void)0)
+#define NMP_PHASE_MAJOR() ((void)0)
 #endif
 
 #define NMP_DEV __device__ __forceinline__
@@ -104,8 +110,13 @@ NMP_DEV float POW4(float x) { float t = x * x; return t * t; }
 NMP_DEV float POW5(float x) { float t = x * x; return x * (t * t); }
 
 // Fortran MIN / MAX / SIGN / ABS
+#if NMP_FASTMATH
+NMP_DEV float MIN(float a, float b) { return fminf(a, b); }  // one FMNMX; differs from the select only for NaN
+NMP_DEV float MAX(float a, float b) { return fmaxf(a, b); }
+#else
 NMP_DEV float MIN(float a, float b) { return (b < a) ? b : a; }
 NMP_DEV float MAX(float a, float b) { return (b > a) ? b : a; }
+#endif
 NMP_DEV float ABS(float a) { return fabsf(a); }
 NMP_DEV float SIGN(float a, float b) { return (b >= 0.0f) ? fabsf(a) : -fabsf(a); }
 
@@ -135,6 +146,20 @@ struct B2 {
   float v[2];
   NMP_DEV float& operator()(int k) { return v[k - 1]; }
   NMP_DEV const float& operator()(int k) const { return v[k - 1]; }
+};
+
+// "Is layer k the top active layer (k == ISNOW+1)?" for a compile-time k, asked through a bit mask whose value is
+// hidden from the optimiser.  Written as `k == ISNOW + 1`, NVVM rewrites the guarded access A(k) into the
+// run-time indexed A(ISNOW+1); one such dynamic index anywhere keeps the whole column structure (~200 words) in
+// local memory instead of registers (profiles/r01_notes.md).
+NMP_DEV unsigned opaque_u(unsigned x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+struct TopLayer {
+  unsigned bit;
+  NMP_DEV explicit TopLayer(int isnow) : bit(opaque_u(1u << (isnow + 3))) {}
+  NMP_DEV bool is(int k) const { return ((bit >> (k + 2)) & 1u) != 0u; }
 };
 
 // ---- physics options ----------------------------------------------------------------------------

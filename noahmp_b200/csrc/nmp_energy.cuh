@@ -923,9 +923,10 @@ NMP_DEV void BARE_FLUX(Ctx& c, const FluxIn& in, float ZPD, float Z0M, float LAT
 // ---- tridiagonal solve: ROSR12 (noahmplsm.F90:5979-6036) on layers NTOP..NSOIL of (-2:4) arrays.
 // P enters as workspace and returns the solution; C(NSOIL) is taken as 0.
 NMP_DEV void ROSR12(L7& P, const L7& A, const L7& B, const L7& C, const L7& D, L7& DELTA, int NTOP) {
+  const TopLayer top(NTOP - 1);
 #pragma unroll
   for (int K = -2; K <= NSOIL; ++K) {
-    if (K == NTOP) {
+    if (top.is(K)) {
       P(K) = -C(K) / B(K);
       DELTA(K) = D(K) / B(K);
     } else if (K > NTOP) {
@@ -949,6 +950,7 @@ NMP_DEV void TSNOSOI(const Ctx& c, int ISNOW, float TBOT, const L7& ZSNSO, float
   L7 AI, BI, CI, RHSTS, DDZ, DTSDZ;
   float ZBOTSNO = ZBOT - SNOWH;
   const int NTOP = ISNOW + 1;
+  const TopLayer top(ISNOW);
   // HRT (:5825-5922); PHI == 0
 #pragma unroll
   for (int K = -2; K <= NSOIL; ++K) {
@@ -958,7 +960,7 @@ NMP_DEV void TSNOSOI(const Ctx& c, int ISNOW, float TBOT, const L7& ZSNSO, float
   for (int K = -2; K <= NSOIL; ++K) {
     if (K >= NTOP) {
       float DENOM, EFLUX;
-      if (K == NTOP) {
+      if (top.is(K)) {
         DENOM = -ZSNSO(K) * HCPCT(K);
         float TEMP1 = -ZSNSO(K + (K < NSOIL ? 1 : 0));
         DDZ(K) = 2.0f / TEMP1;
@@ -979,7 +981,7 @@ NMP_DEV void TSNOSOI(const Ctx& c, int ISNOW, float TBOT, const L7& ZSNSO, float
         }
         EFLUX = (-BOTFLX - DF(K - 1) * DTSDZ(K - 1)) - 0.f;
       }
-      if (K == NTOP) {
+      if (top.is(K)) {
         AI(K) = 0.0f;
         CI(K) = -DF(K) * DDZ(K) / DENOM;
         if (stc == 1) BI(K) = -CI(K);

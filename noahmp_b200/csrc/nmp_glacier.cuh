@@ -388,9 +388,10 @@ NMP_DEV void SNOWWATER_GLACIER(const I7& IMELT, float DT, float SFCTMP, float SN
   DZSNSO(1) = ZSOIL(1);
 #pragma unroll
   for (int IZ = 2; IZ <= NSOIL; ++IZ) DZSNSO(IZ) = (ZSOIL(IZ) - ZSOIL(IZ - 1));
+  const TopLayer top_new(ISNOW);
 #pragma unroll
   for (int IZ = -2; IZ <= NSOIL; ++IZ) {
-    if (IZ == ISNOW + 1) ZSNSO(IZ) = DZSNSO(IZ);
+    if (top_new.is(IZ)) ZSNSO(IZ) = DZSNSO(IZ);
     else if (IZ > ISNOW + 1) ZSNSO(IZ) = ZSNSO(IZ - (IZ > -2 ? 1 : 0)) + DZSNSO(IZ);
   }
 #pragma unroll
@@ -411,10 +412,11 @@ NMP_DEV void NOAHMP_GLACIER(Ctx& c, Col& g) {
   ATM(g.SFCPRS, g.SFCTMP, g.Q2, g.PRCP, g.SOLDN, g.COSZ, THAIR, QAIR, EAIR, RHOAIR, QPRECC, QPRECL, SOLAD, SOLAI,
       SWDOWN);
   const float BEG_WB = g.SNEQV;
+  const TopLayer top0(g.ISNOW);
 #pragma unroll
   for (int IZ = -2; IZ <= NSOIL; ++IZ) {
     DZSNSO(IZ) = 0.f;
-    if (IZ == g.ISNOW + 1) DZSNSO(IZ) = -g.ZSNSO(IZ);
+    if (top0.is(IZ)) DZSNSO(IZ) = -g.ZSNSO(IZ);
     else if (IZ > g.ISNOW + 1) DZSNSO(IZ) = g.ZSNSO(IZ - (IZ > -2 ? 1 : 0)) - g.ZSNSO(IZ);
   }
   // ---- ENERGY_GLACIER ----

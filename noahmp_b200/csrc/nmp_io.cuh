@@ -1,0 +1,28 @@
+// nmp_io.cuh — per-column access to the HBM-resident data from inside the physics.
+//
+// The compact state is a structure of arrays: plane `slot` holds one word per active column, so the accesses
+// of the 32 threads of a warp to one plane are a single unit-stride transaction.  The physics loads a state
+// word as late as it is first needed and stores an output as soon as it is final, which keeps the live
+// register set (and with it the spill traffic) of the 17k-instruction column program small.
+#pragma once
+#include "nmp_common.cuh"
+#include "nmp_fields.h"
+
+namespace nmp {
+
+struct ColumnIO {
+  const nmpf::StepParams& p;
+  long long n;  // compact column
+  int cell;     // grid cell of the column (forcing / static planes are in grid order)
+  bool on;      // stores enabled (false for the padding threads of the last block and for rejected columns)
+  __device__ ColumnIO(const nmpf::StepParams& p_, long long n_, bool on_) : p(p_), n(n_), cell(p_.cell[n_]), on(on_) {}
+  __device__ float forc(int f) const { return __ldg(p.forc[f] + cell); }
+  __device__ float stat(int f) const { return __ldg(p.stat[f] + cell); }
+  __device__ int stati(int f) const { return __float_as_int(__ldg(p.stat[f] + cell)); }
+  __device__ float ld(int slot) const { return p.state[(long long)slot * p.np + n]; }
+  __device__ int ldi(int slot) const { return __float_as_int(p.state[(long long)slot * p.np + n]); }
+  __device__ void st(int slot, float v) const { if (on) p.state[(long long)slot * p.np + n] = v; }
+  __device__ void sti(int slot, int v) const { if (on) p.state[(long long)slot * p.np + n] = __int_as_float(v); }
+};
+
+}  // namespace nmp

@@ -9,25 +9,12 @@
 #include <cstdlib>
 #include "nmp_fields.h"
 #include "nmp_glacier.cuh"
+#include "nmp_io.cuh"
 
 namespace {
 
 using namespace nmp;
 using nmpf::StepParams;
-
-struct ColumnIO {
-  const StepParams& p;
-  long long n;  // compact column
-  int cell;
-  __device__ ColumnIO(const StepParams& p_, long long n_) : p(p_), n(n_), cell(p_.cell[n_]) {}
-  __device__ float forc(int f) const { return __ldg(p.forc[f] + cell); }
-  __device__ float stat(int f) const { return __ldg(p.stat[f] + cell); }
-  __device__ int stati(int f) const { return __float_as_int(__ldg(p.stat[f] + cell)); }
-  __device__ float ld(int slot) const { return p.state[(long long)slot * p.np + n]; }
-  __device__ int ldi(int slot) const { return __float_as_int(p.state[(long long)slot * p.np + n]); }
-  __device__ void st(int slot, float v) const { p.state[(long long)slot * p.np + n] = v; }
-  __device__ void sti(int slot, int v) const { p.state[(long long)slot * p.np + n] = __int_as_float(v); }
-};
 
 __device__ __forceinline__ void report_error(const StepParams& p, int cell, int code, float value) {
   atomicAdd(p.err_count, 1);
@@ -224,7 +211,7 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   // the phase barriers inside NOAHMP_SFLX
   const bool live = t < p.count;
   if (!live) t = p.count - 1;
-  const ColumnIO io(p, (long long)p.first + t);
+  ColumnIO io(p, (long long)p.first + t, live);
   Ctx c;
   init_ctx(c, p);
   Col s;
@@ -235,27 +222,20 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   const int ivg = VEGTYP;
   s.SHDFAC = io.forc(nmpf::FC_VEGFRA) / 100.f;
   s.SHDMAX = io.stat(nmpf::ST_VEGMAX) / 100.f;
-#pragma unroll
-  for (int K = 1; K <= NSOIL; ++K) s.SMCEQ(K) = io.ld(NMP_SLOT(smoiseq) + K - 1);
   s.TV = io.ld(NMP_SLOT(tvxy));
   s.CANLIQ = io.ld(NMP_SLOT(canliqxy));
   s.CANICE = io.ld(NMP_SLOT(canicexy));
   s.EAH = io.ld(NMP_SLOT(eahxy));
   s.TAH = io.ld(NMP_SLOT(tahxy));
   s.FWET = io.ld(NMP_SLOT(fwetxy));
-  s.WSLAKE = io.ld(NMP_SLOT(wslakexy));
-  s.ZWT = io.ld(NMP_SLOT(zwtxy));
-  s.WA = io.ld(NMP_SLOT(waxy));
-  s.WT = io.ld(NMP_SLOT(wtxy));
-  s.LFMASS = io.ld(NMP_SLOT(lfmassxy));
-  s.RTMASS = io.ld(NMP_SLOT(rtmassxy));
-  s.STMASS = io.ld(NMP_SLOT(stmassxy));
-  s.WOOD = io.ld(NMP_SLOT(woodxy));
-  s.STBLCP = io.ld(NMP_SLOT(stblcpxy));
-  s.FASTCP = io.ld(NMP_SLOT(fastcpxy));
+  s.WA = io.ld(NMP_SLOT(waxy));  // for BEG_WB; reloaded with the rest of the water-table state before WATER
   s.LAI = io.ld(NMP_SLOT(xlaixy));
   s.SAI = io.ld(NMP_SLOT(xsaixy));
-  s.SMCWTD = io.ld(NMP_SLOT(smcwtdxy));
+  // WSLAKE (IST = 1 always) and, unless dveg is 2 or 5, the carbon pools pass through NOAHMP_SFLX unchanged:
+  // they stay where they are in HBM.  The remaining state is loaded inside NOAHMP_SFLX where first needed.
+  s.ZWT = 0.f; s.WT = 0.f; s.SMCWTD = 0.f; s.WSLAKE = 0.f;
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) s.SMCEQ(K) = 0.f;
   s.RECH = 0.f;
   s.DEEPRECH = 0.f;
   const float CO2 = 395.e-06f, O2 = 0.209f;
@@ -279,28 +259,12 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
     c.P = c2.P;
     s.VEGTYP = 19;
     s.URBAN = false;
+    io.on = false;
   }
   // every OUT member is assigned by NOAHMP_SFLX before use except on the dveg error path
   s.PONDING = 0.f; s.PONDING1 = 0.f; s.PONDING2 = 0.f; s.QSNBOT = 0.f; s.FPICE = 0.f;
-  NOAHMP_SFLX<O>(c, s);
-
-  ColumnOut o;
-  o.QFX = s.ECAN + s.EDIR + s.ETRAN;
-  o.LH = s.FCEV + s.FGEV + s.FCTR;
-  o.TV = s.TV; o.CANICE = s.CANICE; o.CANLIQ = s.CANLIQ; o.EAH = s.EAH; o.TAH = s.TAH; o.FWET = s.FWET;
-  o.WSLAKE = s.WSLAKE; o.ZWT = s.ZWT; o.WA = s.WA; o.WT = s.WT; o.LFMASS = s.LFMASS; o.RTMASS = s.RTMASS;
-  o.STMASS = s.STMASS; o.WOOD = s.WOOD; o.STBLCP = s.STBLCP; o.FASTCP = s.FASTCP; o.PLAI = s.LAI; o.PSAI = s.SAI;
-  o.T2MV = s.T2MV; o.T2MB = s.T2MB; o.Q2MV = s.Q2V; o.Q2MB = s.Q2B; o.NEE = s.NEE; o.GPP = s.GPP; o.NPP = s.NPP;
-  o.FVEGMP = s.FVEG; o.ECAN = s.ECAN; o.ETRAN = s.ETRAN; o.ESOIL = s.EDIR; o.APAR = s.APAR; o.PSN = s.PSN;
-  o.SAV = s.SAV; o.RSSUN = s.RSSUN; o.RSSHA = s.RSSHA; o.BGAP = s.BGAP; o.WGAP = s.WGAP; o.TGV = s.TGV;
-  o.TGB = s.TGB; o.CHV = s.CHV; o.CHB = s.CHB; o.IRC = s.IRC; o.IRG = s.IRG; o.SHC = s.SHC; o.SHG = s.SHG;
-  o.EVG = s.EVG; o.GHV = s.GHV; o.IRB = s.IRB; o.SHB = s.SHB; o.EVB = s.EVB; o.GHB = s.GHB; o.TR = s.TR;
-  o.EVC = s.EVC; o.CHLEAF = s.CHLEAF; o.CHUC = s.CHUC; o.CHV2 = s.CHV2; o.CHB2 = s.CHB2; o.FSNO = s.FSNO;
-  o.RECH = s.RECH; o.DEEPRECH = s.DEEPRECH; o.SMCWTD = s.SMCWTD;
-  if (live && !bad_index) {
-    store_column(io, p, s, o);
-    if (p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
-  }
+  NOAHMP_SFLX<O>(c, s, io);
+  if (io.on && p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
   if (live && c.err) report_error(p, io.cell, c.err, c.errv);
 }
 
@@ -309,7 +273,7 @@ template <class O>
 __global__ void __launch_bounds__(128) glacier_kernel(const __grid_constant__ StepParams p) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.count) return;
-  const ColumnIO io(p, (long long)p.first + t);
+  const ColumnIO io(p, (long long)p.first + t, true);
   Ctx c;
   init_ctx(c, p);
   Col s;

@@ -2,6 +2,7 @@
 // WATER, CARBON, ERROR) — phys/module_sf_noahmplsm.F90:518-1843, :6382-6613, :9202-9349.
 #pragma once
 #include "nmp_energy.cuh"
+#include "nmp_io.cuh"
 #include "nmp_water.cuh"
 
 namespace nmp {
@@ -281,7 +282,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
     PSNSHA = vo.PSNSHA; s.Q2V = vo.Q2V; s.CHV2 = vo.CAH2; s.CHLEAF = vo.CHLEAF; s.CHUC = vo.CHUC;
   }
 
-  NMP_PHASE();
+  NMP_PHASE_MAJOR();
   s.TGB = s.TG;
   CMB = s.CM;
   s.CHB = s.CH;
@@ -291,7 +292,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
   s.CHB2 = bo.EHB2;
   (void)TAUXV; (void)TAUYV;
 
-  NMP_PHASE();
+  NMP_PHASE_MAJOR();
   if (VEGTILE) {
     s.FIRA = s.FVEG * s.IRG + (1.0f - s.FVEG) * s.IRB + s.IRC;
     s.FSH = s.FVEG * s.SHG + (1.0f - s.FVEG) * s.SHB + s.SHC;
@@ -391,7 +392,7 @@ NMP_DEV void WATER(Ctx& c, Col& s, SflxLocal& L) {
   for (int IZ = 1; IZ <= NSOIL; ++IZ)
     if (IZ <= P.NROOT) ETRANI(IZ) = s.ETRAN * L.BTRANI(IZ) * 0.001f;
 
-  NMP_PHASE();
+  NMP_PHASE_MAJOR();
   SOILWATER<O>(c, s.DT, s.ZSOIL, L.DZSNSO, QINSUR, QSEVA, ETRANI, L.SICE, s.SH2O, s.SMC, s.ZWT, s.URBAN, s.SMCWTD,
                s.DEEPRECH, s.RUNSRF, QDRAIN, s.RUNSUB, WCND, FCRMAX);
   NMP_PHASE();
@@ -412,9 +413,65 @@ NMP_DEV void WATER(Ctx& c, Col& s, SflxLocal& L) {
   s.RUNSUB = s.RUNSUB + SNOFLOW;
 }
 
-// noahmplsm.F90:518-947
+// Scatter of the quantities that are final once ENERGY has run (noahmpdrv.F90:728-835 for these fields).
+// Storing them here, not at the end of the column program, ends their live ranges before WATER / CARBON.
+NMP_DEV void store_energy_outputs(const ColumnIO& io, const Col& s) {
+  io.st(NMP_SLOT(tsk), s.TRAD);
+  io.st(NMP_SLOT(tradxy), s.TRAD);
+  io.st(NMP_SLOT(hfx), s.FSH);
+  io.st(NMP_SLOT(lh), s.FCEV + s.FGEV + s.FCTR);
+  io.st(NMP_SLOT(grdflx), s.SSOIL);
+  io.st(NMP_SLOT(snowc), s.FSNO);
+  io.st(NMP_SLOT(emiss), s.EMISSI);
+  io.st(NMP_SLOT(tgxy), s.TG);
+  io.st(NMP_SLOT(eahxy), s.EAH);
+  io.st(NMP_SLOT(tahxy), s.TAH);
+  io.st(NMP_SLOT(cmxy), s.CM);
+  io.st(NMP_SLOT(chxy), s.CH);
+  io.st(NMP_SLOT(alboldxy), s.ALBOLD);
+  io.st(NMP_SLOT(taussxy), s.TAUSS);
+  io.st(NMP_SLOT(t2mvxy), s.T2MV);
+  io.st(NMP_SLOT(t2mbxy), s.T2MB);
+  io.st(NMP_SLOT(q2mvxy), s.Q2V / (1.0f - s.Q2V));
+  io.st(NMP_SLOT(fvegxy), s.FVEG);
+  io.st(NMP_SLOT(fsaxy), s.FSA);
+  io.st(NMP_SLOT(firaxy), s.FIRA);
+  io.st(NMP_SLOT(aparxy), s.APAR);
+  io.st(NMP_SLOT(psnxy), s.PSN);
+  io.st(NMP_SLOT(savxy), s.SAV);
+  io.st(NMP_SLOT(sagxy), s.SAG);
+  io.st(NMP_SLOT(rssunxy), s.RSSUN);
+  io.st(NMP_SLOT(rsshaxy), s.RSSHA);
+  io.st(NMP_SLOT(bgapxy), s.BGAP);
+  io.st(NMP_SLOT(wgapxy), s.WGAP);
+  io.st(NMP_SLOT(tgvxy), s.TGV);
+  io.st(NMP_SLOT(tgbxy), s.TGB);
+  io.st(NMP_SLOT(chvxy), s.CHV);
+  io.st(NMP_SLOT(chbxy), s.CHB);
+  io.st(NMP_SLOT(ircxy), s.IRC);
+  io.st(NMP_SLOT(irgxy), s.IRG);
+  io.st(NMP_SLOT(shcxy), s.SHC);
+  io.st(NMP_SLOT(shgxy), s.SHG);
+  io.st(NMP_SLOT(evgxy), s.EVG);
+  io.st(NMP_SLOT(ghvxy), s.GHV);
+  io.st(NMP_SLOT(irbxy), s.IRB);
+  io.st(NMP_SLOT(shbxy), s.SHB);
+  io.st(NMP_SLOT(evbxy), s.EVB);
+  io.st(NMP_SLOT(ghbxy), s.GHB);
+  io.st(NMP_SLOT(trxy), s.TR);
+  io.st(NMP_SLOT(evcxy), s.EVC);
+  io.st(NMP_SLOT(chleafxy), s.CHLEAF);
+  io.st(NMP_SLOT(chucxy), s.CHUC);
+  io.st(NMP_SLOT(chv2xy), s.CHV2);
+  io.st(NMP_SLOT(chb2xy), s.CHB2);
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) io.st(NMP_SLOT(tslb) + K - 1, s.STC(K));  // soil temperatures: final after ENERGY
+}
+
+// noahmplsm.F90:518-947, with the dispatcher's scatter of the column (noahmpdrv.F90:713-835) folded in
 template <class O>
-NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
+NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
+  const float DTX = io.p.dt;
   const noahmp_tables& T = *c.T;
   const int dveg = NMP_OPT(dveg);
   SflxLocal L;
@@ -424,10 +481,11 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
   ATM(s.SFCPRS, s.SFCTMP, s.Q2, s.PRCP, s.SOLDN, s.COSZ, L.THAIR, L.QAIR, L.EAIR, L.RHOAIR, L.QPRECC, L.QPRECL,
       L.SOLAD, L.SOLAI, L.SWDOWN);
 
+  const TopLayer top0(s.ISNOW);
 #pragma unroll
   for (int IZ = -2; IZ <= NSOIL; ++IZ) {
     L.DZSNSO(IZ) = 0.f;
-    if (IZ == s.ISNOW + 1) L.DZSNSO(IZ) = -s.ZSNSO(IZ);
+    if (top0.is(IZ)) L.DZSNSO(IZ) = -s.ZSNSO(IZ);
     else if (IZ > s.ISNOW + 1) L.DZSNSO(IZ) = s.ZSNSO(IZ - (IZ > -2 ? 1 : 0)) - s.ZSNSO(IZ);
   }
 
@@ -456,36 +514,58 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
   if (s.URBAN || s.VEGTYP == T.isbarren) s.FVEG = 0.0f;
   if (L.ELAI + L.ESAI == 0.0f) s.FVEG = 0.0f;
 
-  NMP_PHASE();
+  NMP_PHASE_MAJOR();
   ENERGY<O>(c, s, L);
+
+  // the SW and energy-balance checks of ERROR (:1164-1199) depend on ENERGY outputs only; they are evaluated
+  // here (same order of the fatal latch: ERRSW, ERRENG, then ERRWAT after WATER) so those fluxes can be retired
+  s.ERRSW = L.SWDOWN - (s.FSA + s.FSR);
+  if (ABS(s.ERRSW) > 0.01f) c.fatal(NOAHMP_ERR_ERRSW, s.ERRSW);
+  s.ERRENG = s.SAV + s.SAG - (s.FIRA + s.FSH + s.FCEV + s.FGEV + s.FCTR + s.SSOIL);
+  if (ABS(s.ERRENG) > 0.01f) c.fatal(NOAHMP_ERR_ERRENG, s.ERRENG);
+  if (L.SWDOWN != 0.f) s.ALBEDO = s.FSR / L.SWDOWN; else s.ALBEDO = -999.9f;
+  if (s.ALBEDO > -999.f) io.st(NMP_SLOT(albedo), s.ALBEDO);
+  store_energy_outputs(io, s);
 
 #pragma unroll
   for (int IZ = 1; IZ <= NSOIL; ++IZ) L.SICE(IZ) = MAX(0.0f, s.SMC(IZ) - s.SH2O(IZ));
   s.SNEQVO = s.SNEQV;
+  io.st(NMP_SLOT(sneqvoxy), s.SNEQVO);
+
+  // water-table state is first needed here (late load)
+  s.ZWT = io.ld(NMP_SLOT(zwtxy));
+  s.WA = io.ld(NMP_SLOT(waxy));
+  s.WT = io.ld(NMP_SLOT(wtxy));
+  s.SMCWTD = io.ld(NMP_SLOT(smcwtdxy));
+  if (NMP_OPT(run) == 5) {
+#pragma unroll
+    for (int K = 1; K <= NSOIL; ++K) s.SMCEQ(K) = io.ld(NMP_SLOT(smoiseq) + K - 1);
+  }
 
   L.QVAP = MAX(s.FGEV / L.LATHEAG, 0.f);
   L.QDEW = ABS(MIN(s.FGEV / L.LATHEAG, 0.f));
   s.EDIR = L.QVAP - L.QDEW;
 
-  NMP_PHASE();
+  NMP_PHASE_MAJOR();
   WATER<O>(c, s, L);
 
-  NMP_PHASE();
+  NMP_PHASE_MAJOR();
   if (dveg == 2 || dveg == 5) {
+    // carbon pools: loaded here, stored right after (with dveg 1/3/4 they pass through untouched in HBM)
     CarbonState cs;
-    cs.LFMASS = s.LFMASS; cs.RTMASS = s.RTMASS; cs.STMASS = s.STMASS; cs.WOOD = s.WOOD; cs.STBLCP = s.STBLCP;
-    cs.FASTCP = s.FASTCP; cs.LAI = s.LAI; cs.SAI = s.SAI; cs.GPP = s.GPP; cs.NPP = s.NPP; cs.NEE = s.NEE;
+    cs.LFMASS = io.ld(NMP_SLOT(lfmassxy)); cs.RTMASS = io.ld(NMP_SLOT(rtmassxy));
+    cs.STMASS = io.ld(NMP_SLOT(stmassxy)); cs.WOOD = io.ld(NMP_SLOT(woodxy));
+    cs.STBLCP = io.ld(NMP_SLOT(stblcpxy)); cs.FASTCP = io.ld(NMP_SLOT(fastcpxy));
+    cs.LAI = s.LAI; cs.SAI = s.SAI; cs.GPP = s.GPP; cs.NPP = s.NPP; cs.NEE = s.NEE;
     CARBON(c, s.VEGTYP, s.URBAN, L.IGS, s.DT, s.STC(1), s.PSN, s.TV, s.FOLN, L.BTRAN, s.SMC, L.DZSNSO, s.ZSOIL, cs);
-    s.LFMASS = cs.LFMASS; s.RTMASS = cs.RTMASS; s.STMASS = cs.STMASS; s.WOOD = cs.WOOD; s.STBLCP = cs.STBLCP;
-    s.FASTCP = cs.FASTCP; s.LAI = cs.LAI; s.SAI = cs.SAI; s.GPP = cs.GPP; s.NPP = cs.NPP; s.NEE = cs.NEE;
+    io.st(NMP_SLOT(lfmassxy), cs.LFMASS); io.st(NMP_SLOT(rtmassxy), cs.RTMASS);
+    io.st(NMP_SLOT(stmassxy), cs.STMASS); io.st(NMP_SLOT(woodxy), cs.WOOD);
+    io.st(NMP_SLOT(stblcpxy), cs.STBLCP); io.st(NMP_SLOT(fastcpxy), cs.FASTCP);
+    s.LAI = cs.LAI; s.SAI = cs.SAI; s.GPP = cs.GPP; s.NPP = cs.NPP; s.NEE = cs.NEE;
   }
 
-  NMP_PHASE();
-  // ERROR (:1106-1228)
-  s.ERRSW = L.SWDOWN - (s.FSA + s.FSR);
-  if (ABS(s.ERRSW) > 0.01f) c.fatal(NOAHMP_ERR_ERRSW, s.ERRSW);
-  s.ERRENG = s.SAV + s.SAG - (s.FIRA + s.FSH + s.FCEV + s.FGEV + s.FCTR + s.SSOIL);
-  if (ABS(s.ERRENG) > 0.01f) c.fatal(NOAHMP_ERR_ERRENG, s.ERRENG);
+  NMP_PHASE_MAJOR();
+  // ERROR (:1106-1228): water balance (the SW / energy checks ran after ENERGY)
   {
     float END_WB = s.CANLIQ + s.CANICE + s.SNEQV + s.WA;
 #pragma unroll
@@ -503,7 +583,55 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s) {
     s.SNOWH = 0.0f;
     s.SNEQV = 0.0f;
   }
-  if (L.SWDOWN != 0.f) s.ALBEDO = s.FSR / L.SWDOWN; else s.ALBEDO = -999.9f;
+
+  // ---- scatter of everything WATER / CARBON finalised (noahmpdrv.F90:713-835) ----
+  io.st(NMP_SLOT(qfx), s.ECAN + s.EDIR + s.ETRAN);
+  io.st(NMP_SLOT(smstav), 0.0f);
+  io.st(NMP_SLOT(smstot), 0.0f);
+  io.st(NMP_SLOT(sfcrunoff), io.ld(NMP_SLOT(sfcrunoff)) + s.RUNSRF * DTX);
+  io.st(NMP_SLOT(udrunoff), io.ld(NMP_SLOT(udrunoff)) + s.RUNSUB * DTX);
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) {
+    io.st(NMP_SLOT(smois) + K - 1, s.SMC(K));
+    io.st(NMP_SLOT(sh2o) + K - 1, s.SH2O(K));
+  }
+  io.st(NMP_SLOT(snow), s.SNEQV);
+  io.st(NMP_SLOT(snowh), s.SNOWH);
+  io.st(NMP_SLOT(canwat), s.CANLIQ + s.CANICE);
+  io.st(NMP_SLOT(acsnow), io.ld(NMP_SLOT(acsnow)) + s.PRCP * s.FPICE);
+  io.st(NMP_SLOT(acsnom), io.ld(NMP_SLOT(acsnom)) + s.QSNBOT * DTX + s.PONDING + s.PONDING1 + s.PONDING2);
+  io.st(NMP_SLOT(qsfc), s.QSFC);
+  io.sti(NMP_SLOT(isnowxy), s.ISNOW);
+  io.st(NMP_SLOT(tvxy), s.TV);
+  io.st(NMP_SLOT(canliqxy), s.CANLIQ);
+  io.st(NMP_SLOT(canicexy), s.CANICE);
+  io.st(NMP_SLOT(fwetxy), s.FWET);
+  io.st(NMP_SLOT(qsnowxy), s.QSNOW);
+  io.st(NMP_SLOT(zwtxy), s.ZWT);
+  io.st(NMP_SLOT(waxy), s.WA);
+  io.st(NMP_SLOT(wtxy), s.WT);
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) {
+    io.st(NMP_SLOT(tsnoxy) + K + 2, s.STC(K));
+    io.st(NMP_SLOT(snicexy) + K + 2, s.SNICE(K));
+    io.st(NMP_SLOT(snliqxy) + K + 2, s.SNLIQ(K));
+  }
+#pragma unroll
+  for (int K = -2; K <= NSOIL; ++K) io.st(NMP_SLOT(zsnsoxy) + K + 2, s.ZSNSO(K));
+  io.st(NMP_SLOT(xlaixy), s.LAI);
+  io.st(NMP_SLOT(xsaixy), s.SAI);
+  io.st(NMP_SLOT(q2mbxy), s.Q2B / (1.0f - s.Q2B));
+  io.st(NMP_SLOT(neexy), s.NEE);
+  io.st(NMP_SLOT(gppxy), s.GPP);
+  io.st(NMP_SLOT(nppxy), s.NPP);
+  io.st(NMP_SLOT(runsfxy), s.RUNSRF);
+  io.st(NMP_SLOT(runsbxy), s.RUNSUB);
+  io.st(NMP_SLOT(ecanxy), s.ECAN);
+  io.st(NMP_SLOT(edirxy), s.EDIR);
+  io.st(NMP_SLOT(etranxy), s.ETRAN);
+  io.st(NMP_SLOT(rechxy), io.ld(NMP_SLOT(rechxy)) + s.RECH * 1.E3f);
+  io.st(NMP_SLOT(deeprechxy), io.ld(NMP_SLOT(deeprechxy)) + s.DEEPRECH);
+  io.st(NMP_SLOT(smcwtdxy), s.SMCWTD);
 }
 
 }  // namespace nmp

@@ -502,9 +502,10 @@ NMP_DEV void SNOWWATER(const I7& IMELT, float DT, const S4& ZSOIL, float SFCTMP,
   DZSNSO(1) = ZSOIL(1);
 #pragma unroll
   for (int IZ = 2; IZ <= NSOIL; ++IZ) DZSNSO(IZ) = (ZSOIL(IZ) - ZSOIL(IZ - 1));
+  const TopLayer top_new(ISNOW);
 #pragma unroll
   for (int IZ = -2; IZ <= NSOIL; ++IZ) {
-    if (IZ == ISNOW + 1) ZSNSO(IZ) = DZSNSO(IZ);
+    if (top_new.is(IZ)) ZSNSO(IZ) = DZSNSO(IZ);
     else if (IZ > ISNOW + 1) ZSNSO(IZ) = ZSNSO(IZ - (IZ > -2 ? 1 : 0)) + DZSNSO(IZ);
   }
 #pragma unroll
