@@ -289,6 +289,7 @@ def main():
         e_arr = dict(arr)
         for n in out_names:
             e_arr[n] = pinned_out[n].numpy()
+        model.set_fetch(out_names)
         h2d = sum(4 * ni * nj for _ in range(12))
         d2h = 4 * ni * nj * len(out_names)
 
@@ -299,10 +300,7 @@ def main():
                 a[n] = t.numpy()
             s2 = dict(sc)
             s2.update(itimestep=1 + k, yr=yr, julian=float(julian))
-            stt = model.noahmplsm(a, s2)
-            for n in out_names:
-                model.fetch(a, s2, n)
-            return stt
+            return model.noahmplsm(a, s2)  # forcing upload | physics | TSK/HFX/LH/GRDFLX download, pipelined by row chunks
 
         for _ in range(max(1, args.warmup)):
             e2e_step(k); k += 1
@@ -349,7 +347,7 @@ def main():
         if e2e:
             line["e2e"] = {"value": ncol_all * args.steps / e2e_s_max, "unit": "column-steps/s",
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
-                           "call": "noahmp_b200_noahmplsm (RESIDENT) + noahmp_b200_fetch x4, pinned host buffers",
+                           "call": "noahmp_b200_noahmplsm (RESIDENT state, set_fetch=tsk,hfx,lh,grdflx; 8 row chunks), pinned host buffers",
                            "ms_per_step": 1e3 * e2e_s_max / args.steps}
         else:
             line["e2e"] = None

@@ -195,6 +195,14 @@ int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, noa
 /* Refresh the caller's INOUT/OUT host arrays from HBM (RESIDENT mode). */
 int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
 
+/* RESIDENT mode: fields (comma separated noahmp_lsm_args member names, e.g. "tsk,hfx,lh,grdflx"; "" = none) that
+ * every noahmp_b200_noahmplsm call refreshes in the caller's arrays; the rest waits for noahmp_b200_sync_host.
+ * The HRLDAS driver reads TSLB and LAI every step (module_hrldas_noahmp_driver.F90:567-572) and the output list
+ * only every output_timestep (:440-565). */
+int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields);
+/* RESIDENT mode runs as a pipeline over `nchunks` row chunks (forcing upload | physics | result download overlap);
+ * 0 = automatic. */
+int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
 /* Refresh ONE caller array (named like the noahmp_lsm_args member, e.g. "tsk") from HBM in RESIDENT mode. */
 int noahmp_b200_fetch(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, const char* field);
 

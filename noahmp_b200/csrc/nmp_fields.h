@@ -96,4 +96,9 @@ struct StepParams {
   int opt[12];  // dveg crs btr run sfc frz inf rad alb snf tbot stc
 };
 
+// compact-column ranges one launch of the physics covers (a whole tile, or one row chunk of it)
+struct StepRange {
+  int land_first, land_count, glac_first, glac_count;
+};
+
 }  // namespace nmpf

@@ -315,17 +315,18 @@ __global__ void __launch_bounds__(128) glacier_kernel(const __grid_constant__ St
 }
 
 template <class O>
-void launch_pair(const StepParams& base, int nland, int nglac, cudaStream_t stream, long long* launches) {
+void launch_pair(const StepParams& base, const nmpf::StepRange& r, cudaStream_t stream, long long* launches) {
+  const int nland = r.land_count, nglac = r.glac_count;
   if (nland > 0) {
     StepParams p = base;
-    p.first = 0;
+    p.first = r.land_first;
     p.count = nland;
     land_kernel<O><<<(nland + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
     ++*launches;
   }
   if (nglac > 0) {
     StepParams p = base;
-    p.first = nland;
+    p.first = r.glac_first;
     p.count = nglac;
     glacier_kernel<O><<<(nglac + 127) / 128, 128, 0, stream>>>(p);
     ++*launches;
@@ -347,20 +348,20 @@ bool matches(const int* opt) {
 
 // Picks the specialised instantiation when the namelist options match one, else the generic kernel that
 // reads the options at run time.  Returns the name of the variant (for logs / tests).
-const char* launch_step(const StepParams& base, int nland, int nglac, cudaStream_t stream, long long* launches) {
+const char* launch_step(const StepParams& base, const nmpf::StepRange& r, cudaStream_t stream, long long* launches) {
 #ifdef NMP_ONLY_DYNVEG
-  launch_pair<OptDynVeg>(base, nland, nglac, stream, launches);
+  launch_pair<OptDynVeg>(base, r, stream, launches);
   return "dynveg";
 #endif
 #ifndef NMP_NO_SPECIALISE
   if (getenv("NOAHMP_B200_FORCE_RUNTIME")) {
-    launch_pair<OptRuntime>(base, nland, nglac, stream, launches);
+    launch_pair<OptRuntime>(base, r, stream, launches);
     return "runtime";
   }
-  if (matches<OptDefault>(base.opt)) { launch_pair<OptDefault>(base, nland, nglac, stream, launches); return "default"; }
-  if (matches<OptDynVeg>(base.opt)) { launch_pair<OptDynVeg>(base, nland, nglac, stream, launches); return "dynveg"; }
+  if (matches<OptDefault>(base.opt)) { launch_pair<OptDefault>(base, r, stream, launches); return "default"; }
+  if (matches<OptDynVeg>(base.opt)) { launch_pair<OptDynVeg>(base, r, stream, launches); return "dynveg"; }
 #endif
-  launch_pair<OptRuntime>(base, nland, nglac, stream, launches);
+  launch_pair<OptRuntime>(base, r, stream, launches);
   return "runtime";
 }
 

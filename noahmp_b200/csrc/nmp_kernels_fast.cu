@@ -2,7 +2,7 @@
 #define NMP_PARITY 0
 #include "nmp_kernels.cuh"
 
-const char* nmp_launch_step_fast(const nmpf::StepParams& base, int nland, int nglac, cudaStream_t stream,
-                                 long long* launches) {
-  return launch_step(base, nland, nglac, stream, launches);
+const char* nmp_launch_step_fast(const nmpf::StepParams& base, const nmpf::StepRange& r, cudaStream_t stream,
+                                     long long* launches) {
+  return launch_step(base, r, stream, launches);
 }

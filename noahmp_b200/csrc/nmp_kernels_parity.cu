@@ -4,7 +4,7 @@
 #define NMP_PARITY 1
 #include "nmp_kernels.cuh"
 
-const char* nmp_launch_step_parity(const nmpf::StepParams& base, int nland, int nglac, cudaStream_t stream,
-                                   long long* launches) {
-  return launch_step(base, nland, nglac, stream, launches);
+const char* nmp_launch_step_parity(const nmpf::StepParams& base, const nmpf::StepRange& r, cudaStream_t stream,
+                                       long long* launches) {
+  return launch_step(base, r, stream, launches);
 }

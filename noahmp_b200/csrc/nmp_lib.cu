@@ -8,6 +8,7 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,10 +21,8 @@
 using namespace nmpf;
 
 // launchers of the two physics builds (nmp_kernels_fast.cu / nmp_kernels_parity.cu)
-const char* nmp_launch_step_fast(const StepParams& base, int nland, int nglac, cudaStream_t stream,
-                                 long long* launches);
-const char* nmp_launch_step_parity(const StepParams& base, int nland, int nglac, cudaStream_t stream,
-                                   long long* launches);
+const char* nmp_launch_step_fast(const StepParams& base, const StepRange& r, cudaStream_t stream, long long* launches);
+const char* nmp_launch_step_parity(const StepParams& base, const StepRange& r, cudaStream_t stream, long long* launches);
 
 static thread_local std::string g_last_error;
 static void set_error(const std::string& s) { g_last_error = s; }
@@ -91,6 +90,12 @@ struct noahmp_b200_ctx {
   long long launches = 0;
   std::string variant;
   std::unordered_map<const void*, size_t> registered;
+  // chunk pipeline of the RESIDENT-mode call
+  std::vector<int> h_cell;                 // host copy of the column map
+  std::vector<int> fetch;                  // fields refreshed on the host by every noahmplsm call
+  int nchunks = 0;                         // 0 = automatic
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_k;
 };
 
 // ---- small kernels ------------------------------------------------------------------------------------
@@ -129,8 +134,13 @@ __global__ void gather_kernel(const PlaneDesc* __restrict__ planes, const int* _
   state[(long long)d.plane * np + n] = d.grid[(long long)i + (long long)d.layer * ni + (long long)j * ni * d.layers];
 }
 __global__ void scatter_kernel(const PlaneDesc* __restrict__ planes, const int* __restrict__ cell,
-                               const float* __restrict__ state, long long np, int ni) {
+                               const float* __restrict__ state, long long np, int ni, long long first = 0,
+                               long long count = -1) {
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (count >= 0) {
+    if (n >= count) return;
+    n += first;
+  }
   if (n >= np) return;
   const PlaneDesc d = planes[blockIdx.y];
   const int c = cell[n];
@@ -358,6 +368,8 @@ static int classify(noahmp_b200_ctx* ctx) {
     CK(cudaMalloc(&ctx->d_state, sizeof(float) * (size_t)NPLANES * (size_t)ctx->np));
     ctx->np_alloc = ctx->np;
   }
+  ctx->h_cell.resize((size_t)ctx->np);
+  if (ctx->np) CK(cudaMemcpy(ctx->h_cell.data(), ctx->d_cell, sizeof(int) * ctx->np, cudaMemcpyDeviceToHost));
   ctx->classified = true;
   return 0;
 }
@@ -498,6 +510,10 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   cudaFree(ctx->d_vege_iters);
   if (ctx->h_errkey) cudaFreeHost(ctx->h_errkey);
   if (ctx->h_errcount) cudaFreeHost(ctx->h_errcount);
+  for (auto e : ctx->ev_in) cudaEventDestroy(e);
+  for (auto e : ctx->ev_k) cudaEventDestroy(e);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
   delete ctx;
@@ -579,8 +595,9 @@ int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float j
     ctx->launches++;
   }
   const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
-  const char* v = ctx->math_mode == NOAHMP_MATH_PARITY ? nmp_launch_step_parity(p, nland, nglac, s, &ctx->launches)
-                                                       : nmp_launch_step_fast(p, nland, nglac, s, &ctx->launches);
+  const StepRange r{0, nland, nland, nglac};
+  const char* v = ctx->math_mode == NOAHMP_MATH_PARITY ? nmp_launch_step_parity(p, r, s, &ctx->launches)
+                                                       : nmp_launch_step_fast(p, r, s, &ctx->launches);
   ctx->variant = v;
   if (nsea > 0) {
     seaice_kernel<<<(nsea + 255) / 256, 256, 0, s>>>(ctx->d_state, ctx->d_cell, ctx->d_stat[ST_XICE], ctx->np, nland + nglac,
@@ -613,17 +630,167 @@ int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
   return 0;
 }
 
+// H2D of rows [j0, j1) of one forcing plane
+static int h2d_rows(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, int kms, int lev, int j0, int j1,
+                    cudaStream_t st) {
+  const size_t ni = ctx->ni;
+  if (nk == 1) {
+    CK(cudaMemcpyAsync(dst + (size_t)j0 * ni, src + (size_t)j0 * ni, sizeof(float) * ni * (j1 - j0), cudaMemcpyHostToDevice, st));
+  } else {
+    CK(cudaMemcpy2DAsync(dst + (size_t)j0 * ni, sizeof(float) * ni, src + (size_t)j0 * ni * nk + (size_t)(lev - kms) * ni,
+                         sizeof(float) * ni * nk, sizeof(float) * ni, j1 - j0, cudaMemcpyHostToDevice, st));
+  }
+  return 0;
+}
+
+// RESIDENT-mode step as a row-chunk pipeline: while chunk c is computed, the forcing rows of chunk c+1 are on
+// their way up and the requested result fields of chunk c-1 on their way down (three streams, events in between).
+// Columns of a class are stored in grid order, so a row chunk is one contiguous compact range per class.
+static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, int nchunks) {
+  const int nk = a->kme - a->kms + 1, kms = a->kms, ni = ctx->ni, nj = ctx->nj;
+  if (!ctx->s_in) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  while ((int)ctx->ev_in.size() < nchunks) {
+    cudaEvent_t e1, e2;
+    CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    ctx->ev_in.push_back(e1);
+    ctx->ev_k.push_back(e2);
+  }
+  struct Plane { int id; const float* src; int nk, lev; };
+  const Plane planes[NFORC] = {
+      {FC_COSZIN, a->coszin, 1, 1}, {FC_T, a->t3d, nk, 1},       {FC_QV, a->qv3d, nk, 1},      {FC_U, a->u_phy, nk, 1},
+      {FC_V, a->v_phy, nk, 1},      {FC_SWDOWN, a->swdown, 1, 1}, {FC_GLW, a->glw, 1, 1},      {FC_P1, a->p8w3d, nk, a->kts},
+      {FC_P2, a->p8w3d, nk, a->kts + 1}, {FC_RAINBL, a->rainbl, 1, 1}, {FC_VEGFRA, a->vegfra, 1, 1}, {FC_DZ8W, a->dz8w, nk, 1}};
+  for (const Plane& pl : planes) pin(ctx, pl.src, sizeof(float) * (size_t)ni * nj * pl.nk);
+  for (int f : ctx->fetch) pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
+
+  StepParams p = ctx->base;
+  p.itimestep = a->itimestep;
+  p.yearlen = year_length(a->yr);
+  p.julian = a->julian;
+  p.dt = a->dt;
+  cudaStream_t sk = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), sk));
+  CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), sk));
+  if (a->itimestep == 1 && ctx->nclass[CL_WATER] > 0) {
+    const int T = 256;
+    first_step_water_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, sk>>>(
+        ctx->d_stat[ST_XLAND], ctx->d_stat[ST_XICE], ctx->d_grid[F_smstav], ctx->d_grid[F_smstot], ctx->d_grid[F_smois],
+        ctx->d_grid[F_tslb], ctx->ni, ctx->ncell);
+    ctx->launches++;
+  }
+  const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
+  const int* cl = ctx->h_cell.data();
+  auto lower = [&](int lo, int hi, int cell) {  // first compact index in [lo,hi) whose cell >= `cell`
+    return (int)(std::lower_bound(cl + lo, cl + hi, cell) - cl);
+  };
+  for (int c = 0; c < nchunks; ++c) {
+    const int j0 = (int)((long long)nj * c / nchunks), j1 = (int)((long long)nj * (c + 1) / nchunks);
+    if (j1 <= j0) continue;
+    for (const Plane& pl : planes) {
+      int rc = h2d_rows(ctx, ctx->d_forc[pl.id], pl.src, pl.nk, kms, pl.lev, j0, j1, ctx->s_in);
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    CK(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
+    const int c0 = j0 * ni, c1 = j1 * ni;
+    StepRange r;
+    r.land_first = lower(0, nland, c0);
+    r.land_count = lower(0, nland, c1) - r.land_first;
+    r.glac_first = lower(nland, nland + nglac, c0);
+    r.glac_count = lower(nland, nland + nglac, c1) - r.glac_first;
+    const char* v = ctx->math_mode == NOAHMP_MATH_PARITY ? nmp_launch_step_parity(p, r, sk, &ctx->launches)
+                                                         : nmp_launch_step_fast(p, r, sk, &ctx->launches);
+    ctx->variant = v;
+    const int s0 = lower(nland + nglac, nland + nglac + nsea, c0), s1 = lower(nland + nglac, nland + nglac + nsea, c1);
+    if (s1 > s0) {
+      seaice_kernel<<<(s1 - s0 + 255) / 256, 256, 0, sk>>>(ctx->d_state, ctx->d_cell, ctx->d_stat[ST_XICE], ctx->np, s0,
+                                                         s1 - s0, a->itimestep);
+      ctx->launches++;
+    }
+    if (!ctx->fetch.empty()) {
+      // scatter the requested fields of this chunk's columns into the grid-order staging, then send the rows down
+      const int T = 256;
+      const int rng[3][2] = {{r.land_first, r.land_count}, {r.glac_first, r.glac_count}, {s0, s1 - s0}};
+      for (int f : ctx->fetch) {
+        for (auto& q : rng) {
+          if (q[1] <= 0) continue;
+          dim3 grid((unsigned)((q[1] + T - 1) / T), kFields[f].layers);
+          scatter_kernel<<<grid, T, 0, sk>>>(ctx->d_planes + kSlots.slot[f], ctx->d_cell, ctx->d_state, ctx->np, ctx->ni,
+                                              (long long)q[0], (long long)q[1]);
+          ctx->launches++;
+        }
+      }
+      CK(cudaEventRecord(ctx->ev_k[c], sk));
+      CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
+      for (int f : ctx->fetch) {
+        const size_t L = kFields[f].layers, off = (size_t)j0 * ni * L, cnt = (size_t)(j1 - j0) * ni * L;
+        CK(cudaMemcpyAsync(host_ptr(a, f) + off, ctx->d_grid[f] + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost,
+                           ctx->s_out));
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_errkey, ctx->d_errkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sk));
+  CK(cudaMemcpyAsync(ctx->h_errcount, ctx->d_errcount, sizeof(int), cudaMemcpyDeviceToHost, sk));
+  CK(cudaStreamSynchronize(sk));
+  if (!ctx->fetch.empty()) CK(cudaStreamSynchronize(ctx->s_out));
+  return 0;
+}
+
+// Fields (comma separated noahmp_lsm_args member names, "" = none) that every RESIDENT-mode noahmplsm call
+// refreshes in the caller's host arrays, e.g. "tsk,hfx,lh,grdflx"; everything else waits for sync_host().
+int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields) {
+  if (!ctx || !fields) return NOAHMP_ERR_ARG;
+  std::vector<int> list;
+  std::string s(fields), tok;
+  size_t pos = 0;
+  while (pos <= s.size()) {
+    size_t e = s.find(',', pos);
+    if (e == std::string::npos) e = s.size();
+    tok = s.substr(pos, e - pos);
+    pos = e + 1;
+    while (!tok.empty() && tok.front() == ' ') tok.erase(0, 1);
+    while (!tok.empty() && tok.back() == ' ') tok.pop_back();
+    if (tok.empty()) continue;
+    int f = 0;
+    for (; f < NFIELDS; ++f)
+      if (tok == kFields[f].name) break;
+    if (f == NFIELDS) { set_error("unknown field " + tok); return NOAHMP_ERR_ARG; }
+    list.push_back(f);
+  }
+  ctx->fetch = list;
+  return 0;
+}
+
+// Number of row chunks of the RESIDENT-mode pipeline (0 = automatic: 1 below 2^20 cells, else 8).
+int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks) {
+  if (!ctx || nchunks < 0 || nchunks > 64) return NOAHMP_ERR_ARG;
+  ctx->nchunks = nchunks;
+  return 0;
+}
+
 int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp_status* status) {
   if (!ctx || !a) return NOAHMP_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   int rc;
   if (ctx->sync_mode == NOAHMP_SYNC_FULL || !ctx->uploaded) {
     if ((rc = noahmp_b200_upload(ctx, a))) { if (status) { status->code = rc; status->count = 0; } return rc; }
-  } else {
+  }
+  if (ctx->sync_mode == NOAHMP_SYNC_RESIDENT) {
     if ((rc = check_bounds(ctx, a))) return rc;
     fill_scalars(ctx, a);
     if ((rc = check_options(ctx))) return rc;
-    if ((rc = upload_forcing(ctx, a))) return rc;
+    int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 8 : 1);
+    if (nch > ctx->nj) nch = ctx->nj;
+    if ((rc = step_resident_pipelined(ctx, a, nch))) return rc;
+    noahmp_status st;
+    decode_status(ctx, &st);
+    if (status) *status = st;
+    return st.code;
   }
   if ((rc = noahmp_b200_step_device(ctx, a->itimestep, a->yr, a->julian, a->dt, nullptr))) return rc;
   if (ctx->sync_mode == NOAHMP_SYNC_FULL) {

@@ -120,6 +120,13 @@ class NoahMP:
             arr = (C.c_void_p * 12)(*[int(p) for p in ptrs])
             self._check(self._L.noahmp_b200_bind_forcing(self._ctx, arr))
 
+    def set_fetch(self, fields=()):
+        """Fields every RESIDENT-mode noahmplsm() call refreshes on the host (pipelined with the step)."""
+        self._check(self._L.noahmp_b200_set_fetch(self._ctx, ",".join(fields).encode()))
+
+    def set_chunks(self, n):
+        self._check(self._L.noahmp_b200_set_chunks(self._ctx, n))
+
     def fetch(self, arrays, scalars, field):
         a = _capi.make_args(arrays, scalars)
         self._check(self._L.noahmp_b200_fetch(self._ctx, C.byref(a), field.encode()))

@@ -166,19 +166,30 @@ def test_fast_math_within_tolerance(built, tables_usgs):
     m.close()
 
 
-def test_resident_mode_equals_full_sync(built, tables_usgs):
-    """State kept in HBM across steps (forcing-only upload) ends bit-identical to the strict drop-in mode."""
+@pytest.mark.parametrize("chunks", [1, 5])
+def test_resident_mode_equals_full_sync(built, tables_usgs, chunks):
+    """State kept in HBM across steps (forcing-only upload, row-chunk pipeline, per-call fetch list) ends
+    bit-identical to the strict drop-in mode, and the fetched fields are current after every call."""
     import noahmp_b200
     cfg = _cfg("C4", 160, 120)
     _, st, state0 = make_case(cfg, tables_usgs)
+    st["xice"][30:34, 10:70] = 1.0  # sea-ice cells too
     a, b = clone_state(state0), clone_state(state0)
     m1 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST, sync=noahmp_b200.SYNC_FULL)
     m2 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST, sync=noahmp_b200.SYNC_RESIDENT)
-    run_gpu(m1, cfg, st, a, 10)
-    run_gpu(m2, cfg, st, b, 10)
-    assert diff_report(a, state0)  # FULL mode moved the host arrays
+    m2.set_chunks(chunks)
+    m2.set_fetch(["tsk", "tslb", "isnowxy"])
     xp = S.backend()
-    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 10, st), b, 10)
+    for step in range(1, 9):
+        frc = S.forcing(xp, cfg, step, st)
+        arr_a, sc = S.args_from(cfg, st, frc, a, step)
+        arr_b, _ = S.args_from(cfg, st, frc, b, step)
+        s1, s2 = m1.noahmplsm(arr_a, sc), m2.noahmplsm(arr_b, sc)
+        assert (s1.code, s1.count) == (s2.code, s2.count) == (0, 0)
+        for n in ("tsk", "tslb", "isnowxy"):
+            assert np.array_equal(a[n], b[n]), (step, n)
+    assert diff_report(a, b, ["hfx", "smois", "snow"])  # not fetched: still the initial host values
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 8, st), b, 8)
     m2.sync_host(arr, sc)
     rep = diff_report(a, b)
     assert not rep, rep
