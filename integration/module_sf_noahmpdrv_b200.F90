@@ -1,0 +1,604 @@
+!> module_sf_noahmpdrv_b200.F90 -- drop-in replacement of the `noahmplsm` grid loop of
+!> phys/module_sf_noahmpdrv.F90:11-844 that forwards to libnoahmp_b200.so (include/noahmp_b200.h).
+!>
+!> The SUBROUTINE keeps the reference's name, dummy-argument list and order, so
+!> driver/module_hrldas_noahmp_driver.F90:386-415 compiles and calls it unchanged.  Build: rename the
+!> reference's `noahmplsm` (or drop its body), add this file to phys/Makefile, link with
+!> -lnoahmp_b200 -lcudart -lstdc++.  NOT compiled in the build image of this repo (no Fortran compiler there).
+!> Member and argument order follow noahmp_b200/_capi.py:ARGS_SPEC (= the struct in the header).
+MODULE module_sf_noahmpdrv_b200
+  USE, INTRINSIC :: ISO_C_BINDING
+  IMPLICIT NONE
+  PRIVATE
+  PUBLIC :: noahmplsm, noahmp_b200_start, noahmp_b200_stop, noahmp_b200_refresh_host
+
+  !> mirrors `noahmp_lsm_args` member for member
+  TYPE, BIND(C) :: noahmp_lsm_args
+    INTEGER(C_INT) :: itimestep
+    INTEGER(C_INT) :: yr
+    REAL(C_FLOAT) :: julian
+    TYPE(C_PTR) :: coszin
+    TYPE(C_PTR) :: xlatin
+    TYPE(C_PTR) :: dz8w
+    REAL(C_FLOAT) :: dt
+    TYPE(C_PTR) :: dzs
+    INTEGER(C_INT) :: nsoil
+    REAL(C_FLOAT) :: dx
+    TYPE(C_PTR) :: ivgtyp
+    TYPE(C_PTR) :: isltyp
+    TYPE(C_PTR) :: vegfra
+    TYPE(C_PTR) :: vegmax
+    TYPE(C_PTR) :: tmn
+    TYPE(C_PTR) :: xland
+    TYPE(C_PTR) :: xice
+    REAL(C_FLOAT) :: xice_thres
+    INTEGER(C_INT) :: isice
+    INTEGER(C_INT) :: isurban
+    INTEGER(C_INT) :: idveg
+    INTEGER(C_INT) :: iopt_crs
+    INTEGER(C_INT) :: iopt_btr
+    INTEGER(C_INT) :: iopt_run
+    INTEGER(C_INT) :: iopt_sfc
+    INTEGER(C_INT) :: iopt_frz
+    INTEGER(C_INT) :: iopt_inf
+    INTEGER(C_INT) :: iopt_rad
+    INTEGER(C_INT) :: iopt_alb
+    INTEGER(C_INT) :: iopt_snf
+    INTEGER(C_INT) :: iopt_tbot
+    INTEGER(C_INT) :: iopt_stc
+    INTEGER(C_INT) :: iz0tlnd
+    TYPE(C_PTR) :: t3d
+    TYPE(C_PTR) :: qv3d
+    TYPE(C_PTR) :: u_phy
+    TYPE(C_PTR) :: v_phy
+    TYPE(C_PTR) :: swdown
+    TYPE(C_PTR) :: glw
+    TYPE(C_PTR) :: p8w3d
+    TYPE(C_PTR) :: rainbl
+    TYPE(C_PTR) :: tsk
+    TYPE(C_PTR) :: hfx
+    TYPE(C_PTR) :: qfx
+    TYPE(C_PTR) :: lh
+    TYPE(C_PTR) :: grdflx
+    TYPE(C_PTR) :: smstav
+    TYPE(C_PTR) :: smstot
+    TYPE(C_PTR) :: sfcrunoff
+    TYPE(C_PTR) :: udrunoff
+    TYPE(C_PTR) :: albedo
+    TYPE(C_PTR) :: snowc
+    TYPE(C_PTR) :: smois
+    TYPE(C_PTR) :: sh2o
+    TYPE(C_PTR) :: tslb
+    TYPE(C_PTR) :: snow
+    TYPE(C_PTR) :: snowh
+    TYPE(C_PTR) :: canwat
+    TYPE(C_PTR) :: acsnom
+    TYPE(C_PTR) :: acsnow
+    TYPE(C_PTR) :: emiss
+    TYPE(C_PTR) :: qsfc
+    TYPE(C_PTR) :: isnowxy
+    TYPE(C_PTR) :: tvxy
+    TYPE(C_PTR) :: tgxy
+    TYPE(C_PTR) :: canicexy
+    TYPE(C_PTR) :: canliqxy
+    TYPE(C_PTR) :: eahxy
+    TYPE(C_PTR) :: tahxy
+    TYPE(C_PTR) :: cmxy
+    TYPE(C_PTR) :: chxy
+    TYPE(C_PTR) :: fwetxy
+    TYPE(C_PTR) :: sneqvoxy
+    TYPE(C_PTR) :: alboldxy
+    TYPE(C_PTR) :: qsnowxy
+    TYPE(C_PTR) :: wslakexy
+    TYPE(C_PTR) :: zwtxy
+    TYPE(C_PTR) :: waxy
+    TYPE(C_PTR) :: wtxy
+    TYPE(C_PTR) :: tsnoxy
+    TYPE(C_PTR) :: zsnsoxy
+    TYPE(C_PTR) :: snicexy
+    TYPE(C_PTR) :: snliqxy
+    TYPE(C_PTR) :: lfmassxy
+    TYPE(C_PTR) :: rtmassxy
+    TYPE(C_PTR) :: stmassxy
+    TYPE(C_PTR) :: woodxy
+    TYPE(C_PTR) :: stblcpxy
+    TYPE(C_PTR) :: fastcpxy
+    TYPE(C_PTR) :: xlaixy
+    TYPE(C_PTR) :: xsaixy
+    TYPE(C_PTR) :: taussxy
+    TYPE(C_PTR) :: smoiseq
+    TYPE(C_PTR) :: smcwtdxy
+    TYPE(C_PTR) :: deeprechxy
+    TYPE(C_PTR) :: rechxy
+    TYPE(C_PTR) :: t2mvxy
+    TYPE(C_PTR) :: t2mbxy
+    TYPE(C_PTR) :: q2mvxy
+    TYPE(C_PTR) :: q2mbxy
+    TYPE(C_PTR) :: tradxy
+    TYPE(C_PTR) :: neexy
+    TYPE(C_PTR) :: gppxy
+    TYPE(C_PTR) :: nppxy
+    TYPE(C_PTR) :: fvegxy
+    TYPE(C_PTR) :: runsfxy
+    TYPE(C_PTR) :: runsbxy
+    TYPE(C_PTR) :: ecanxy
+    TYPE(C_PTR) :: edirxy
+    TYPE(C_PTR) :: etranxy
+    TYPE(C_PTR) :: fsaxy
+    TYPE(C_PTR) :: firaxy
+    TYPE(C_PTR) :: aparxy
+    TYPE(C_PTR) :: psnxy
+    TYPE(C_PTR) :: savxy
+    TYPE(C_PTR) :: sagxy
+    TYPE(C_PTR) :: rssunxy
+    TYPE(C_PTR) :: rsshaxy
+    TYPE(C_PTR) :: bgapxy
+    TYPE(C_PTR) :: wgapxy
+    TYPE(C_PTR) :: tgvxy
+    TYPE(C_PTR) :: tgbxy
+    TYPE(C_PTR) :: chvxy
+    TYPE(C_PTR) :: chbxy
+    TYPE(C_PTR) :: shgxy
+    TYPE(C_PTR) :: shcxy
+    TYPE(C_PTR) :: shbxy
+    TYPE(C_PTR) :: evgxy
+    TYPE(C_PTR) :: evbxy
+    TYPE(C_PTR) :: ghvxy
+    TYPE(C_PTR) :: ghbxy
+    TYPE(C_PTR) :: irgxy
+    TYPE(C_PTR) :: ircxy
+    TYPE(C_PTR) :: irbxy
+    TYPE(C_PTR) :: trxy
+    TYPE(C_PTR) :: evcxy
+    TYPE(C_PTR) :: chleafxy
+    TYPE(C_PTR) :: chucxy
+    TYPE(C_PTR) :: chv2xy
+    TYPE(C_PTR) :: chb2xy
+    INTEGER(C_INT) :: ids
+    INTEGER(C_INT) :: ide
+    INTEGER(C_INT) :: jds
+    INTEGER(C_INT) :: jde
+    INTEGER(C_INT) :: kds
+    INTEGER(C_INT) :: kde
+    INTEGER(C_INT) :: ims
+    INTEGER(C_INT) :: ime
+    INTEGER(C_INT) :: jms
+    INTEGER(C_INT) :: jme
+    INTEGER(C_INT) :: kms
+    INTEGER(C_INT) :: kme
+    INTEGER(C_INT) :: its
+    INTEGER(C_INT) :: ite
+    INTEGER(C_INT) :: jts
+    INTEGER(C_INT) :: jte
+    INTEGER(C_INT) :: kts
+    INTEGER(C_INT) :: kte
+  END TYPE noahmp_lsm_args
+
+  TYPE, BIND(C) :: noahmp_status
+    INTEGER(C_INT) :: code, i, j, count
+    REAL(C_FLOAT)  :: value
+  END TYPE noahmp_status
+
+  INTEGER(C_INT), PARAMETER :: NOAHMP_SYNC_FULL = 0, NOAHMP_SYNC_RESIDENT = 1
+  INTEGER, PARAMETER :: NOAHMP_TABLES_BYTES = 12712   ! sizeof(noahmp_tables); checked at start-up
+
+  TYPE(C_PTR), SAVE :: ctx = C_NULL_PTR
+  INTEGER(C_INT8_T), SAVE, TARGET :: tables(NOAHMP_TABLES_BYTES)
+  TYPE(noahmp_lsm_args), SAVE :: last_args
+
+  INTERFACE
+    FUNCTION noahmp_b200_read_tables(dir, dataset, soil, tbl) BIND(C, NAME="noahmp_b200_read_tables") RESULT(rc)
+      IMPORT; CHARACTER(KIND=C_CHAR), INTENT(IN) :: dir(*), dataset(*), soil(*); TYPE(C_PTR), VALUE :: tbl
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_sizeof_tables() BIND(C, NAME="noahmp_b200_sizeof_tables") RESULT(n)
+      IMPORT; INTEGER(C_LONG_LONG) :: n
+    END FUNCTION
+    FUNCTION noahmp_b200_create(device, tbl, ni, nj) BIND(C, NAME="noahmp_b200_create") RESULT(c)
+      IMPORT; INTEGER(C_INT), VALUE :: device, ni, nj; TYPE(C_PTR), VALUE :: tbl; TYPE(C_PTR) :: c
+    END FUNCTION
+    SUBROUTINE noahmp_b200_destroy(c) BIND(C, NAME="noahmp_b200_destroy")
+      IMPORT; TYPE(C_PTR), VALUE :: c
+    END SUBROUTINE
+    FUNCTION noahmp_b200_set_mode(c, mode) BIND(C, NAME="noahmp_b200_set_mode") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT), VALUE :: mode; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_set_fetch(c, fields) BIND(C, NAME="noahmp_b200_set_fetch") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; CHARACTER(KIND=C_CHAR), INTENT(IN) :: fields(*); INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_noahmplsm(c, args, st) BIND(C, NAME="noahmp_b200_noahmplsm") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_lsm_args), INTENT(IN) :: args; TYPE(noahmp_status) :: st
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_sync_host(c, args) BIND(C, NAME="noahmp_b200_sync_host") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_lsm_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
+    END FUNCTION
+  END INTERFACE
+
+CONTAINS
+
+  !> once, after read_mp_veg_parameters / SOIL_VEG_GEN_PARM would have run (they read the same files from the CWD)
+  SUBROUTINE noahmp_b200_start(mminlu, ni, nj, device, resident)
+    CHARACTER(LEN=*), INTENT(IN) :: mminlu
+    INTEGER, INTENT(IN) :: ni, nj, device
+    LOGICAL, INTENT(IN) :: resident
+    INTEGER(C_INT) :: rc
+    IF (noahmp_b200_sizeof_tables() /= NOAHMP_TABLES_BYTES) CALL wrf_error_fatal("noahmp_b200: table ABI mismatch")
+    rc = noahmp_b200_read_tables("."//C_NULL_CHAR, TRIM(mminlu)//C_NULL_CHAR, "STAS"//C_NULL_CHAR, C_LOC(tables))
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: cannot read MPTABLE/VEGPARM/SOILPARM/GENPARM.TBL")
+    ctx = noahmp_b200_create(INT(device, C_INT), C_LOC(tables), INT(ni, C_INT), INT(nj, C_INT))
+    IF (.NOT. C_ASSOCIATED(ctx)) CALL wrf_error_fatal("noahmp_b200: no usable CUDA device (there is no CPU fallback)")
+    IF (resident) THEN
+      rc = noahmp_b200_set_mode(ctx, NOAHMP_SYNC_RESIDENT)
+      rc = noahmp_b200_set_fetch(ctx, "tslb,xlaixy"//C_NULL_CHAR)   ! what land_driver_exe prints every step (:567-572)
+    END IF
+  END SUBROUTINE noahmp_b200_start
+
+  !> RESIDENT mode: call before hrldas_output / restart writes (driver :440-592) to refresh every host array
+  SUBROUTINE noahmp_b200_refresh_host()
+    INTEGER(C_INT) :: rc
+    rc = noahmp_b200_sync_host(ctx, last_args)
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: sync_host failed")
+  END SUBROUTINE noahmp_b200_refresh_host
+
+  SUBROUTINE noahmp_b200_stop()
+    CALL noahmp_b200_destroy(ctx)
+    ctx = C_NULL_PTR
+  END SUBROUTINE noahmp_b200_stop
+
+  SUBROUTINE noahmplsm( &
+      ITIMESTEP, YR, JULIAN, COSZIN, XLATIN, DZ8W, DT, DZS, NSOIL, DX, IVGTYP, ISLTYP, VEGFRA, &
+      VEGMAX, TMN, XLAND, XICE, XICE_THRES, ISICE, ISURBAN, IDVEG, IOPT_CRS, IOPT_BTR, IOPT_RUN, &
+      IOPT_SFC, IOPT_FRZ, IOPT_INF, IOPT_RAD, IOPT_ALB, IOPT_SNF, IOPT_TBOT, IOPT_STC, IZ0TLND, &
+      T3D, QV3D, U_PHY, V_PHY, SWDOWN, GLW, P8W3D, RAINBL, TSK, HFX, QFX, LH, GRDFLX, SMSTAV, &
+      SMSTOT, SFCRUNOFF, UDRUNOFF, ALBEDO, SNOWC, SMOIS, SH2O, TSLB, SNOW, SNOWH, CANWAT, ACSNOM, &
+      ACSNOW, EMISS, QSFC, ISNOWXY, TVXY, TGXY, CANICEXY, CANLIQXY, EAHXY, TAHXY, CMXY, CHXY, &
+      FWETXY, SNEQVOXY, ALBOLDXY, QSNOWXY, WSLAKEXY, ZWTXY, WAXY, WTXY, TSNOXY, ZSNSOXY, SNICEXY, &
+      SNLIQXY, LFMASSXY, RTMASSXY, STMASSXY, WOODXY, STBLCPXY, FASTCPXY, XLAIXY, XSAIXY, TAUSSXY, &
+      SMOISEQ, SMCWTDXY, DEEPRECHXY, RECHXY, T2MVXY, T2MBXY, Q2MVXY, Q2MBXY, TRADXY, NEEXY, GPPXY, &
+      NPPXY, FVEGXY, RUNSFXY, RUNSBXY, ECANXY, EDIRXY, ETRANXY, FSAXY, FIRAXY, APARXY, PSNXY, &
+      SAVXY, SAGXY, RSSUNXY, RSSHAXY, BGAPXY, WGAPXY, TGVXY, TGBXY, CHVXY, CHBXY, SHGXY, SHCXY, &
+      SHBXY, EVGXY, EVBXY, GHVXY, GHBXY, IRGXY, IRCXY, IRBXY, TRXY, EVCXY, CHLEAFXY, CHUCXY, &
+      CHV2XY, CHB2XY, IDS, IDE, JDS, JDE, KDS, KDE, IMS, IME, JMS, JME, KMS, KME, ITS, ITE, JTS, &
+      JTE, KTS, KTE)
+    IMPLICIT NONE
+    INTEGER, INTENT(IN) :: ITIMESTEP
+    INTEGER, INTENT(IN) :: YR
+    REAL, INTENT(IN) :: JULIAN
+    REAL, INTENT(IN) :: DT
+    INTEGER, INTENT(IN) :: NSOIL
+    REAL, INTENT(IN) :: DX
+    REAL, INTENT(IN) :: XICE_THRES
+    INTEGER, INTENT(IN) :: ISICE
+    INTEGER, INTENT(IN) :: ISURBAN
+    INTEGER, INTENT(IN) :: IDVEG
+    INTEGER, INTENT(IN) :: IOPT_CRS
+    INTEGER, INTENT(IN) :: IOPT_BTR
+    INTEGER, INTENT(IN) :: IOPT_RUN
+    INTEGER, INTENT(IN) :: IOPT_SFC
+    INTEGER, INTENT(IN) :: IOPT_FRZ
+    INTEGER, INTENT(IN) :: IOPT_INF
+    INTEGER, INTENT(IN) :: IOPT_RAD
+    INTEGER, INTENT(IN) :: IOPT_ALB
+    INTEGER, INTENT(IN) :: IOPT_SNF
+    INTEGER, INTENT(IN) :: IOPT_TBOT
+    INTEGER, INTENT(IN) :: IOPT_STC
+    INTEGER, INTENT(IN) :: IZ0TLND
+    INTEGER, INTENT(IN) :: IDS
+    INTEGER, INTENT(IN) :: IDE
+    INTEGER, INTENT(IN) :: JDS
+    INTEGER, INTENT(IN) :: JDE
+    INTEGER, INTENT(IN) :: KDS
+    INTEGER, INTENT(IN) :: KDE
+    INTEGER, INTENT(IN) :: IMS
+    INTEGER, INTENT(IN) :: IME
+    INTEGER, INTENT(IN) :: JMS
+    INTEGER, INTENT(IN) :: JME
+    INTEGER, INTENT(IN) :: KMS
+    INTEGER, INTENT(IN) :: KME
+    INTEGER, INTENT(IN) :: ITS
+    INTEGER, INTENT(IN) :: ITE
+    INTEGER, INTENT(IN) :: JTS
+    INTEGER, INTENT(IN) :: JTE
+    INTEGER, INTENT(IN) :: KTS
+    INTEGER, INTENT(IN) :: KTE
+    REAL, INTENT(IN), TARGET :: COSZIN(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: XLATIN(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: DZ8W(ims:ime, kms:kme, jms:jme)
+    REAL, INTENT(IN), TARGET :: DZS(1:NSOIL)
+    INTEGER, INTENT(IN), TARGET :: IVGTYP(ims:ime, jms:jme)
+    INTEGER, INTENT(IN), TARGET :: ISLTYP(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: VEGFRA(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: VEGMAX(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: TMN(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: XLAND(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: XICE(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: T3D(ims:ime, kms:kme, jms:jme)
+    REAL, INTENT(IN), TARGET :: QV3D(ims:ime, kms:kme, jms:jme)
+    REAL, INTENT(IN), TARGET :: U_PHY(ims:ime, kms:kme, jms:jme)
+    REAL, INTENT(IN), TARGET :: V_PHY(ims:ime, kms:kme, jms:jme)
+    REAL, INTENT(IN), TARGET :: SWDOWN(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: GLW(ims:ime, jms:jme)
+    REAL, INTENT(IN), TARGET :: P8W3D(ims:ime, kms:kme, jms:jme)
+    REAL, INTENT(IN), TARGET :: RAINBL(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TSK(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: HFX(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: QFX(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: LH(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: GRDFLX(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SMSTAV(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SMSTOT(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SFCRUNOFF(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: UDRUNOFF(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ALBEDO(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SNOWC(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SMOIS(ims:ime, 1:NSOIL, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SH2O(ims:ime, 1:NSOIL, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TSLB(ims:ime, 1:NSOIL, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SNOW(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SNOWH(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CANWAT(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ACSNOM(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ACSNOW(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: EMISS(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: QSFC(ims:ime, jms:jme)
+    INTEGER, INTENT(INOUT), TARGET :: ISNOWXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TGXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CANICEXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CANLIQXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: EAHXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TAHXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CMXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: FWETXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SNEQVOXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ALBOLDXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: QSNOWXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: WSLAKEXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ZWTXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: WAXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: WTXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TSNOXY(ims:ime, -2:0, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ZSNSOXY(ims:ime, -2:NSOIL, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SNICEXY(ims:ime, -2:0, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SNLIQXY(ims:ime, -2:0, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: LFMASSXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: RTMASSXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: STMASSXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: WOODXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: STBLCPXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: FASTCPXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: XLAIXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: XSAIXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TAUSSXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SMOISEQ(ims:ime, 1:NSOIL, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SMCWTDXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: DEEPRECHXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: RECHXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: T2MVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: T2MBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: Q2MVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: Q2MBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TRADXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: NEEXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: GPPXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: NPPXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: FVEGXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: RUNSFXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: RUNSBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ECANXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: EDIRXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: ETRANXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: FSAXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: FIRAXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: APARXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: PSNXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SAVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SAGXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: RSSUNXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: RSSHAXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: BGAPXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: WGAPXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TGVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TGBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SHGXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SHCXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: SHBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: EVGXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: EVBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: GHVXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: GHBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: IRGXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: IRCXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: IRBXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: TRXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: EVCXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHLEAFXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHUCXY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHV2XY(ims:ime, jms:jme)
+    REAL, INTENT(INOUT), TARGET :: CHB2XY(ims:ime, jms:jme)
+    TYPE(noahmp_lsm_args) :: a
+    TYPE(noahmp_status) :: st
+    INTEGER(C_INT) :: rc
+    CHARACTER(LEN=160) :: msg
+
+    a%itimestep = ITIMESTEP
+    a%yr = YR
+    a%julian = JULIAN
+    a%coszin = C_LOC(COSZIN)
+    a%xlatin = C_LOC(XLATIN)
+    a%dz8w = C_LOC(DZ8W)
+    a%dt = DT
+    a%dzs = C_LOC(DZS)
+    a%nsoil = NSOIL
+    a%dx = DX
+    a%ivgtyp = C_LOC(IVGTYP)
+    a%isltyp = C_LOC(ISLTYP)
+    a%vegfra = C_LOC(VEGFRA)
+    a%vegmax = C_LOC(VEGMAX)
+    a%tmn = C_LOC(TMN)
+    a%xland = C_LOC(XLAND)
+    a%xice = C_LOC(XICE)
+    a%xice_thres = XICE_THRES
+    a%isice = ISICE
+    a%isurban = ISURBAN
+    a%idveg = IDVEG
+    a%iopt_crs = IOPT_CRS
+    a%iopt_btr = IOPT_BTR
+    a%iopt_run = IOPT_RUN
+    a%iopt_sfc = IOPT_SFC
+    a%iopt_frz = IOPT_FRZ
+    a%iopt_inf = IOPT_INF
+    a%iopt_rad = IOPT_RAD
+    a%iopt_alb = IOPT_ALB
+    a%iopt_snf = IOPT_SNF
+    a%iopt_tbot = IOPT_TBOT
+    a%iopt_stc = IOPT_STC
+    a%iz0tlnd = IZ0TLND
+    a%t3d = C_LOC(T3D)
+    a%qv3d = C_LOC(QV3D)
+    a%u_phy = C_LOC(U_PHY)
+    a%v_phy = C_LOC(V_PHY)
+    a%swdown = C_LOC(SWDOWN)
+    a%glw = C_LOC(GLW)
+    a%p8w3d = C_LOC(P8W3D)
+    a%rainbl = C_LOC(RAINBL)
+    a%tsk = C_LOC(TSK)
+    a%hfx = C_LOC(HFX)
+    a%qfx = C_LOC(QFX)
+    a%lh = C_LOC(LH)
+    a%grdflx = C_LOC(GRDFLX)
+    a%smstav = C_LOC(SMSTAV)
+    a%smstot = C_LOC(SMSTOT)
+    a%sfcrunoff = C_LOC(SFCRUNOFF)
+    a%udrunoff = C_LOC(UDRUNOFF)
+    a%albedo = C_LOC(ALBEDO)
+    a%snowc = C_LOC(SNOWC)
+    a%smois = C_LOC(SMOIS)
+    a%sh2o = C_LOC(SH2O)
+    a%tslb = C_LOC(TSLB)
+    a%snow = C_LOC(SNOW)
+    a%snowh = C_LOC(SNOWH)
+    a%canwat = C_LOC(CANWAT)
+    a%acsnom = C_LOC(ACSNOM)
+    a%acsnow = C_LOC(ACSNOW)
+    a%emiss = C_LOC(EMISS)
+    a%qsfc = C_LOC(QSFC)
+    a%isnowxy = C_LOC(ISNOWXY)
+    a%tvxy = C_LOC(TVXY)
+    a%tgxy = C_LOC(TGXY)
+    a%canicexy = C_LOC(CANICEXY)
+    a%canliqxy = C_LOC(CANLIQXY)
+    a%eahxy = C_LOC(EAHXY)
+    a%tahxy = C_LOC(TAHXY)
+    a%cmxy = C_LOC(CMXY)
+    a%chxy = C_LOC(CHXY)
+    a%fwetxy = C_LOC(FWETXY)
+    a%sneqvoxy = C_LOC(SNEQVOXY)
+    a%alboldxy = C_LOC(ALBOLDXY)
+    a%qsnowxy = C_LOC(QSNOWXY)
+    a%wslakexy = C_LOC(WSLAKEXY)
+    a%zwtxy = C_LOC(ZWTXY)
+    a%waxy = C_LOC(WAXY)
+    a%wtxy = C_LOC(WTXY)
+    a%tsnoxy = C_LOC(TSNOXY)
+    a%zsnsoxy = C_LOC(ZSNSOXY)
+    a%snicexy = C_LOC(SNICEXY)
+    a%snliqxy = C_LOC(SNLIQXY)
+    a%lfmassxy = C_LOC(LFMASSXY)
+    a%rtmassxy = C_LOC(RTMASSXY)
+    a%stmassxy = C_LOC(STMASSXY)
+    a%woodxy = C_LOC(WOODXY)
+    a%stblcpxy = C_LOC(STBLCPXY)
+    a%fastcpxy = C_LOC(FASTCPXY)
+    a%xlaixy = C_LOC(XLAIXY)
+    a%xsaixy = C_LOC(XSAIXY)
+    a%taussxy = C_LOC(TAUSSXY)
+    a%smoiseq = C_LOC(SMOISEQ)
+    a%smcwtdxy = C_LOC(SMCWTDXY)
+    a%deeprechxy = C_LOC(DEEPRECHXY)
+    a%rechxy = C_LOC(RECHXY)
+    a%t2mvxy = C_LOC(T2MVXY)
+    a%t2mbxy = C_LOC(T2MBXY)
+    a%q2mvxy = C_LOC(Q2MVXY)
+    a%q2mbxy = C_LOC(Q2MBXY)
+    a%tradxy = C_LOC(TRADXY)
+    a%neexy = C_LOC(NEEXY)
+    a%gppxy = C_LOC(GPPXY)
+    a%nppxy = C_LOC(NPPXY)
+    a%fvegxy = C_LOC(FVEGXY)
+    a%runsfxy = C_LOC(RUNSFXY)
+    a%runsbxy = C_LOC(RUNSBXY)
+    a%ecanxy = C_LOC(ECANXY)
+    a%edirxy = C_LOC(EDIRXY)
+    a%etranxy = C_LOC(ETRANXY)
+    a%fsaxy = C_LOC(FSAXY)
+    a%firaxy = C_LOC(FIRAXY)
+    a%aparxy = C_LOC(APARXY)
+    a%psnxy = C_LOC(PSNXY)
+    a%savxy = C_LOC(SAVXY)
+    a%sagxy = C_LOC(SAGXY)
+    a%rssunxy = C_LOC(RSSUNXY)
+    a%rsshaxy = C_LOC(RSSHAXY)
+    a%bgapxy = C_LOC(BGAPXY)
+    a%wgapxy = C_LOC(WGAPXY)
+    a%tgvxy = C_LOC(TGVXY)
+    a%tgbxy = C_LOC(TGBXY)
+    a%chvxy = C_LOC(CHVXY)
+    a%chbxy = C_LOC(CHBXY)
+    a%shgxy = C_LOC(SHGXY)
+    a%shcxy = C_LOC(SHCXY)
+    a%shbxy = C_LOC(SHBXY)
+    a%evgxy = C_LOC(EVGXY)
+    a%evbxy = C_LOC(EVBXY)
+    a%ghvxy = C_LOC(GHVXY)
+    a%ghbxy = C_LOC(GHBXY)
+    a%irgxy = C_LOC(IRGXY)
+    a%ircxy = C_LOC(IRCXY)
+    a%irbxy = C_LOC(IRBXY)
+    a%trxy = C_LOC(TRXY)
+    a%evcxy = C_LOC(EVCXY)
+    a%chleafxy = C_LOC(CHLEAFXY)
+    a%chucxy = C_LOC(CHUCXY)
+    a%chv2xy = C_LOC(CHV2XY)
+    a%chb2xy = C_LOC(CHB2XY)
+    a%ids = IDS
+    a%ide = IDE
+    a%jds = JDS
+    a%jde = JDE
+    a%kds = KDS
+    a%kde = KDE
+    a%ims = IMS
+    a%ime = IME
+    a%jms = JMS
+    a%jme = JME
+    a%kms = KMS
+    a%kme = KME
+    a%its = ITS
+    a%ite = ITE
+    a%jts = JTS
+    a%jte = JTE
+    a%kts = KTS
+    a%kte = KTE
+    last_args = a
+    rc = noahmp_b200_noahmplsm(ctx, a, st)
+    IF (rc /= 0) THEN
+      ! same fatal convention as the reference (util/module_wrf_utilities.F:12-24), same message texts
+      SELECT CASE (st%code)
+      CASE (1); WRITE(msg, '(A,2I6,ES14.6)') "Stop in Noah-MP (ERRSW) at i,j: ", st%i, st%j, st%value
+      CASE (2); WRITE(msg, '(A,2I6,ES14.6)') "Energy budget problem in NOAHMP LSM at i,j: ", st%i, st%j, st%value
+      CASE (3); WRITE(msg, '(A,2I6,ES14.6)') "Water budget problem in NOAHMP LSM at i,j: ", st%i, st%j, st%value
+      CASE (4); WRITE(msg, '(A,2I6)') "STOP in Noah-MP: emitted longwave <0 at i,j: ", st%i, st%j
+      CASE (5); WRITE(msg, '(A,2I6)') "CRITICAL PROBLEM: HCAN <= ZPD at i,j: ", st%i, st%j
+      CASE (6); WRITE(msg, '(A,2I6)') "STOP in Noah-MP: ZLVL <= ZPD at i,j: ", st%i, st%j
+      CASE (7); WRITE(msg, '(A,2I6)') "Warning: too many input soil/landuse types or NROOT at i,j: ", st%i, st%j
+      CASE DEFAULT; WRITE(msg, '(A,I6)') "noahmp_b200 failure, code ", rc
+      END SELECT
+      CALL wrf_error_fatal(TRIM(msg))
+    END IF
+  END SUBROUTINE noahmplsm
+
+END MODULE module_sf_noahmpdrv_b200
