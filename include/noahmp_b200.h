@@ -239,6 +239,43 @@ float* noahmp_b200_device_state(noahmp_b200_ctx* ctx, const char* field, int lay
 int noahmp_b200_enable_iteration_counts(noahmp_b200_ctx* ctx, int enable);
 int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out);
 
+/* ---- opt_run = 5: Miguez-Macho & Fan groundwater, replaces `CALL WTABLE_mmf_noahmp(...)` ----------------------
+ * phys/module_sf_noahmp_groundwater.F90:14-198 (LATERALFLOW :201-295, UPDATEWTD :298-606), called by
+ * land_driver_exe every STEPWTD steps (driver/module_hrldas_noahmp_driver.F90:420-436).  One member per dummy
+ * argument, same names, same order; 2-D arrays (ims:ime,jms:jme), 3-D (ims:ime,1:nsoil,jms:jme). */
+typedef struct noahmp_wtable_args {
+  int32_t nsoil;
+  const float *xland, *xice;
+  float xice_threshold;
+  int32_t isice;
+  const int32_t* isltyp;
+  const float* smoiseq;
+  const float* dzs;
+  float wtddt; /* minutes */
+  const float *fdepth, *area, *topo;
+  int32_t isurban;
+  const int32_t* ivgtyp;
+  const float *rivercond, *riverbed, *eqwtd, *pexp;
+  float *smois, *sh2oxy, *smcwtd, *wtd, *qrf, *deeprech, *qspring, *qslat, *qrfs, *qsprings, *rech;
+  int32_t ids, ide, jds, jde, kds, kde;
+  int32_t ims, ime, jms, jme, kms, kme;
+  int32_t its, ite, jts, jte, kts, kte;
+} noahmp_wtable_args;
+
+/* Whole call on one tile.  SYNC_FULL: uploads the INOUT arrays, downloads INOUT+OUT.  SYNC_RESIDENT: SMOIS, SH2O,
+ * SMCWTD, WTD (= ZWTXY), DEEPRECH, RECH are the planes the resident noahmplsm state already holds; the other
+ * arrays are uploaded on the first call and kept on the device (sync with noahmp_b200_wtable_sync_host).
+ * With ids..ide / jds..jde describing the GLOBAL domain and its..ite / jts..jte the tile, a tile whose neighbours
+ * are other GPUs needs its halo filled between _begin and _end (below); noahmp_b200_wtable = _begin + _end. */
+int noahmp_b200_wtable(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
+int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
+int noahmp_b200_wtable_end(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
+/* Device planes of KCELL and HEAD (LATERALFLOW pass 1) with a one-cell halo ring: (nj+2) rows of (ni+2) floats,
+ * element (i - its + 1) + (j - jts + 1) * (ni + 2).  The caller exchanges the ring with the neighbouring tiles
+ * (NCCL send/recv through its own communicator) between _begin and _end. */
+int noahmp_b200_wtable_halo(noahmp_b200_ctx* ctx, float** kcell, float** head);
+int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
+
 /* ---- domain decomposition: replaces mpp_land_partition arithmetic ----------------------------
  * mpp/module_mpp_land.F90:124-141 (process grid), :245-288 (tile extents). All 1-based inclusive. */
 void noahmp_b200_proc_grid(int nproc, int* nprocx, int* nprocy);

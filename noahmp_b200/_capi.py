@@ -142,3 +142,34 @@ def tables_to_dict(t):
         v = getattr(t, name)
         d[name] = v if ctype in (_i, _f) else np.array(np.ctypeslib.as_array(v))
     return d
+
+
+# ---- opt_run = 5 groundwater: noahmp_wtable_args (WTABLE_mmf_noahmp dummy list, groundwater.F90:14-22) -----------
+WT_SPEC = (
+    [("nsoil", "i"), ("xland", "pf"), ("xice", "pf"), ("xice_threshold", "f"), ("isice", "i"), ("isltyp", "pi"),
+     ("smoiseq", "pf"), ("dzs", "pf"), ("wtddt", "f"), ("fdepth", "pf"), ("area", "pf"), ("topo", "pf"),
+     ("isurban", "i"), ("ivgtyp", "pi"), ("rivercond", "pf"), ("riverbed", "pf"), ("eqwtd", "pf"), ("pexp", "pf")]
+    + [(n, "pf") for n in "smois sh2oxy smcwtd wtd qrf deeprech qspring qslat qrfs qsprings rech".split()]
+    + [(n, "i") for n in _BOUNDS]
+)
+WT_STATIC = ["fdepth", "area", "topo", "rivercond", "riverbed", "eqwtd", "pexp"]
+WT_INOUT = ["smois", "sh2oxy", "smcwtd", "wtd", "deeprech", "qslat", "qrfs", "qsprings", "rech"]
+WT_OUT = ["qrf", "qspring"]
+
+
+class NoahmpWtableArgs(C.Structure):
+    _fields_ = [(n, _K[k]) for n, k in WT_SPEC]
+
+
+def make_wtable_args(arrays, scalars):
+    a = NoahmpWtableArgs()
+    for n, k in WT_SPEC:
+        if k in ("i", "f"):
+            setattr(a, n, scalars[n])
+        else:
+            arr = arrays[n]
+            want = np.int32 if k == "pi" else np.float32
+            if arr.dtype != want or not arr.flags["C_CONTIGUOUS"]:
+                raise TypeError(f"{n}: need C-contiguous {want.__name__}, got {arr.dtype}")
+            setattr(a, n, arr.ctypes.data_as(_K[k]))
+    return a

@@ -17,6 +17,7 @@ _LIB = None
 _pa = C.POINTER(_capi.NoahmpLsmArgs)
 _pt = C.POINTER(_capi.NoahmpTables)
 _ps = C.POINTER(_capi.NoahmpStatus)
+_pw = C.POINTER(_capi.NoahmpWtableArgs)
 _ctx = C.c_void_p
 
 # name -> (restype, argtypes); every symbol include/noahmp_b200.h declares
@@ -47,6 +48,11 @@ SYMBOLS = {
     "noahmp_b200_device_state": (C.c_void_p, [_ctx, C.c_char_p, C.c_int, C.POINTER(C.c_longlong)]),
     "noahmp_b200_enable_iteration_counts": (C.c_int, [_ctx, C.c_int]),
     "noahmp_b200_get_iteration_counts": (C.c_int, [_ctx, C.POINTER(C.c_int32)]),
+    "noahmp_b200_wtable": (C.c_int, [_ctx, _pw]),
+    "noahmp_b200_wtable_begin": (C.c_int, [_ctx, _pw]),
+    "noahmp_b200_wtable_end": (C.c_int, [_ctx, _pw]),
+    "noahmp_b200_wtable_halo": (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "noahmp_b200_wtable_sync_host": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_proc_grid": (None, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "noahmp_b200_tile": (None, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
 }

@@ -96,6 +96,24 @@ struct StepParams {
   int opt[12];  // dveg crs btr run sfc frz inf rad alb snf tbot stc
 };
 
+// kernel parameter block of the opt_run=5 groundwater step (nmp_groundwater.cuh)
+struct WtParams {
+  const float *fdepth, *area, *topo, *rivercond, *riverbed, *eqwtd, *pexp;  // grid-order planes
+  const float *isltyp, *ivgtyp;                                           // int32 bit patterns
+  const float* wtd_grid;                                                  // WTD of every cell (staging plane of ZWTXY)
+  float *qrf, *qspring, *qslat, *qrfs, *qsprings;                         // grid-order planes
+  float *kcell, *head;                                                    // (ni+2) x (nj+2), one-cell halo ring
+  float* state;
+  const int* cell;
+  const noahmp_tables* tables;
+  long long np;
+  int nland, ni, nj;
+  int ids, ide, jds, jde, its, ite, jts, jte;
+  int isurban;
+  float deltat;
+  float dzs[NOAHMP_NSOIL];
+};
+
 // compact-column ranges one launch of the physics covers (a whole tile, or one row chunk of it)
 struct StepRange {
   int land_first, land_count, glac_first, glac_count;

@@ -3,8 +3,13 @@
 // -ffp-contract=off).  Only the run-time-option instantiation is built here.
 #define NMP_PARITY 1
 #include "nmp_kernels.cuh"
+#include "nmp_groundwater.cuh"
 
 const char* nmp_launch_step_parity(const nmpf::StepParams& base, const nmpf::StepRange& r, cudaStream_t stream,
                                        long long* launches) {
   return launch_step(base, r, stream, launches);
+}
+
+void nmp_launch_wtable_parity(const nmpf::WtParams& w, cudaStream_t stream, long long* launches, int phase) {
+  launch_wtable(w, stream, launches, phase);
 }

@@ -23,6 +23,8 @@ using namespace nmpf;
 // launchers of the two physics builds (nmp_kernels_fast.cu / nmp_kernels_parity.cu)
 const char* nmp_launch_step_fast(const StepParams& base, const StepRange& r, cudaStream_t stream, long long* launches);
 const char* nmp_launch_step_parity(const StepParams& base, const StepRange& r, cudaStream_t stream, long long* launches);
+void nmp_launch_wtable_fast(const WtParams& w, cudaStream_t stream, long long* launches, int phase);
+void nmp_launch_wtable_parity(const WtParams& w, cudaStream_t stream, long long* launches, int phase);
 
 static thread_local std::string g_last_error;
 static void set_error(const std::string& s) { g_last_error = s; }
@@ -96,6 +98,10 @@ struct noahmp_b200_ctx {
   int nchunks = 0;                         // 0 = automatic
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_k;
+  // opt_run = 5 groundwater: grid-order planes (see WtPlane) and the haloed KCELL / HEAD planes
+  float* d_wt[12] = {};
+  float *d_kcell = nullptr, *d_head = nullptr;
+  bool wt_init = false;
 };
 
 // ---- small kernels ------------------------------------------------------------------------------------
@@ -508,6 +514,8 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   cudaFree(ctx->d_state); cudaFree(ctx->d_planes); cudaFree(ctx->d_cell); cudaFree(ctx->d_class);
   cudaFree(ctx->d_cub); cudaFree(ctx->d_nsel); cudaFree(ctx->d_errkey); cudaFree(ctx->d_errcount);
   cudaFree(ctx->d_vege_iters);
+  for (auto p : ctx->d_wt) cudaFree(p);
+  cudaFree(ctx->d_kcell); cudaFree(ctx->d_head);
   if (ctx->h_errkey) cudaFreeHost(ctx->h_errkey);
   if (ctx->h_errcount) cudaFreeHost(ctx->h_errcount);
   for (auto e : ctx->ev_in) cudaEventDestroy(e);
@@ -836,6 +844,205 @@ int noahmp_b200_bind_forcing(noahmp_b200_ctx* ctx, float* const* dev_ptrs) {
   if (!ctx) return NOAHMP_ERR_ARG;
   for (int f = 0; f < NFORC; ++f) ctx->base.forc[f] = dev_ptrs ? dev_ptrs[f] : ctx->d_forc[f];
   return 0;
+}
+
+// ---- opt_run = 5 groundwater step ---------------------------------------------------------------------------
+enum WtPlane { WT_FDEPTH = 0, WT_AREA, WT_TOPO, WT_RIVERCOND, WT_RIVERBED, WT_EQWTD, WT_PEXP, WT_QRF, WT_QSPRING,
+               WT_QSLAT, WT_QRFS, WT_QSPRINGS, NWT };
+
+// non-land bookkeeping of WTABLE_mmf_noahmp's last loops (:112-129, :186-195): QRF = 0 (QSPRING, INTENT(OUT) and
+// never assigned there in the reference, is defined as 0), RECH += DEEPRECH*1e3, DEEPRECH = 0
+__global__ void wt_nonland_cells_kernel(const unsigned char* __restrict__ cls, float* qrf, float* qspring,
+                                        float* rech_grid, float* deeprech_grid, long long ncell) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const unsigned char k = cls[c];
+  if (k == CL_LAND) return;
+  qrf[c] = 0.f;
+  qspring[c] = 0.f;
+  if (k == CL_WATER) {  // cells without a compact column: their accumulators live in the grid-order arrays
+    rech_grid[c] = rech_grid[c] + deeprech_grid[c] * 1.E3f;
+    deeprech_grid[c] = 0.f;
+  }
+}
+__global__ void wt_nonland_cols_kernel(float* state, long long np, int first, int count) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  long long n = (long long)first + t;
+  float* rech = state + (long long)NMP_SLOT(rechxy) * np;
+  float* deep = state + (long long)NMP_SLOT(deeprechxy) * np;
+  rech[n] = rech[n] + deep[n] * 1.E3f;
+  deep[n] = 0.f;
+}
+
+struct WtField { int f; size_t off; };
+static const WtField kWtInout[] = {{F_smois, offsetof(noahmp_wtable_args, smois)},
+                                   {F_sh2o, offsetof(noahmp_wtable_args, sh2oxy)},
+                                   {F_smcwtdxy, offsetof(noahmp_wtable_args, smcwtd)},
+                                   {F_zwtxy, offsetof(noahmp_wtable_args, wtd)},
+                                   {F_deeprechxy, offsetof(noahmp_wtable_args, deeprech)},
+                                   {F_rechxy, offsetof(noahmp_wtable_args, rech)}};
+static inline float* wt_ptr(const noahmp_wtable_args* a, size_t off) {
+  return *reinterpret_cast<float* const*>(reinterpret_cast<const char*>(a) + off);
+}
+
+static int wt_check(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  if (!ctx || !a) return NOAHMP_ERR_ARG;
+  if (!ctx->uploaded) { set_error("wtable before the state was uploaded (call noahmplsm or upload first)"); return NOAHMP_ERR_ARG; }
+  if (a->ims != a->its || a->ime != a->ite || a->jms != a->jts || a->jme != a->jte ||
+      a->ite - a->its + 1 != ctx->ni || a->jte - a->jts + 1 != ctx->nj || a->nsoil != NOAHMP_NSOIL) {
+    set_error("wtable: memory bounds must equal tile bounds and match the context");
+    return NOAHMP_ERR_ARG;
+  }
+  return 0;
+}
+
+static int gather_field(noahmp_b200_ctx* ctx, int f) {
+  if (ctx->np == 0) return 0;
+  const int T = 256;
+  dim3 grid((unsigned)((ctx->np + T - 1) / T), kFields[f].layers);
+  gather_kernel<<<grid, T, 0, ctx->stream>>>(ctx->d_planes + kSlots.slot[f], ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
+  ctx->launches++;
+  return 0;
+}
+static int scatter_field(noahmp_b200_ctx* ctx, int f) {
+  if (ctx->np == 0) return 0;
+  const int T = 256;
+  dim3 grid((unsigned)((ctx->np + T - 1) / T), kFields[f].layers);
+  scatter_kernel<<<grid, T, 0, ctx->stream>>>(ctx->d_planes + kSlots.slot[f], ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
+  ctx->launches++;
+  return 0;
+}
+
+static void wt_params(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a, WtParams& w) {
+  w.fdepth = ctx->d_wt[WT_FDEPTH]; w.area = ctx->d_wt[WT_AREA]; w.topo = ctx->d_wt[WT_TOPO];
+  w.rivercond = ctx->d_wt[WT_RIVERCOND]; w.riverbed = ctx->d_wt[WT_RIVERBED]; w.eqwtd = ctx->d_wt[WT_EQWTD];
+  w.pexp = ctx->d_wt[WT_PEXP];
+  w.isltyp = ctx->d_stat[ST_ISLTYP]; w.ivgtyp = ctx->d_stat[ST_IVGTYP];
+  w.wtd_grid = ctx->d_grid[F_zwtxy];
+  w.qrf = ctx->d_wt[WT_QRF]; w.qspring = ctx->d_wt[WT_QSPRING]; w.qslat = ctx->d_wt[WT_QSLAT];
+  w.qrfs = ctx->d_wt[WT_QRFS]; w.qsprings = ctx->d_wt[WT_QSPRINGS];
+  w.kcell = ctx->d_kcell; w.head = ctx->d_head;
+  w.state = ctx->d_state; w.cell = ctx->d_cell; w.tables = ctx->d_tables; w.np = ctx->np;
+  w.nland = ctx->nclass[CL_LAND]; w.ni = ctx->ni; w.nj = ctx->nj;
+  w.ids = a->ids; w.ide = a->ide; w.jds = a->jds; w.jde = a->jde;
+  w.its = a->its; w.ite = a->ite; w.jts = a->jts; w.jte = a->jte;
+  w.isurban = a->isurban;
+  w.deltat = a->wtddt * 60.f;
+  for (int k = 0; k < NOAHMP_NSOIL; ++k) w.dzs[k] = a->dzs[k];
+}
+
+int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  int rc = wt_check(ctx, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t plane = sizeof(float) * ctx->ncell, halo = sizeof(float) * (size_t)(ctx->ni + 2) * (ctx->nj + 2);
+  if (!ctx->d_kcell) {
+    for (int k = 0; k < NWT; ++k) {
+      CK(cudaMalloc(&ctx->d_wt[k], plane));
+      CK(cudaMemsetAsync(ctx->d_wt[k], 0, plane, ctx->stream));
+    }
+    CK(cudaMalloc(&ctx->d_kcell, halo));
+    CK(cudaMalloc(&ctx->d_head, halo));
+  }
+  const bool full = ctx->sync_mode == NOAHMP_SYNC_FULL;
+  if (full || !ctx->wt_init) {
+    const float* src[NWT] = {a->fdepth, a->area, a->topo, a->rivercond, a->riverbed, a->eqwtd, a->pexp, nullptr, nullptr,
+                             a->qslat, a->qrfs, a->qsprings};
+    for (int k = 0; k < NWT; ++k)
+      if (src[k]) { pin(ctx, src[k], plane); CK(cudaMemcpyAsync(ctx->d_wt[k], src[k], plane, cudaMemcpyHostToDevice, ctx->stream)); }
+    // SMOISEQ is static input of the scheme
+    pin(ctx, a->smoiseq, plane * NOAHMP_NSOIL);
+    CK(cudaMemcpyAsync(ctx->d_grid[F_smoiseq], a->smoiseq, plane * NOAHMP_NSOIL, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = gather_field(ctx, F_smoiseq))) return rc;
+    ctx->wt_init = true;
+  }
+  if (full) {
+    for (const WtField& wf : kWtInout) {
+      const size_t bytes = plane * kFields[wf.f].layers;
+      pin(ctx, wt_ptr(a, wf.off), bytes);
+      CK(cudaMemcpyAsync(ctx->d_grid[wf.f], wt_ptr(a, wf.off), bytes, cudaMemcpyHostToDevice, ctx->stream));
+      if ((rc = gather_field(ctx, wf.f))) return rc;
+    }
+  } else {
+    CK(cudaDeviceSynchronize());  // resident steps may have run on a caller stream
+    if ((rc = scatter_field(ctx, F_zwtxy))) return rc;  // WTD of every cell in grid order for the stencil
+  }
+  CK(cudaMemsetAsync(ctx->d_kcell, 0, halo, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_head, 0, halo, ctx->stream));
+  WtParams w;
+  wt_params(ctx, a, w);
+  if (ctx->math_mode == NOAHMP_MATH_PARITY) nmp_launch_wtable_parity(w, ctx->stream, &ctx->launches, 0);
+  else nmp_launch_wtable_fast(w, ctx->stream, &ctx->launches, 0);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // the halo exchange that may follow runs on the caller's stream
+  return 0;
+}
+
+int noahmp_b200_wtable_halo(noahmp_b200_ctx* ctx, float** kcell, float** head) {
+  if (!ctx || !ctx->d_kcell || !kcell || !head) return NOAHMP_ERR_ARG;
+  *kcell = ctx->d_kcell;
+  *head = ctx->d_head;
+  return 0;
+}
+
+static int wt_download(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  const size_t plane = sizeof(float) * ctx->ncell;
+  int rc;
+  for (const WtField& wf : kWtInout) {
+    if ((rc = scatter_field(ctx, wf.f))) return rc;
+    const size_t bytes = plane * kFields[wf.f].layers;
+    pin(ctx, wt_ptr(a, wf.off), bytes);
+    CK(cudaMemcpyAsync(wt_ptr(a, wf.off), ctx->d_grid[wf.f], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  float* dst[5] = {a->qrf, a->qspring, a->qslat, a->qrfs, a->qsprings};
+  const int src[5] = {WT_QRF, WT_QSPRING, WT_QSLAT, WT_QRFS, WT_QSPRINGS};
+  for (int k = 0; k < 5; ++k) {
+    pin(ctx, dst[k], plane);
+    CK(cudaMemcpyAsync(dst[k], ctx->d_wt[src[k]], plane, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int noahmp_b200_wtable_end(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  int rc = wt_check(ctx, a);
+  if (rc) return rc;
+  if (!ctx->d_kcell) { set_error("wtable_end before wtable_begin"); return NOAHMP_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());  // halo writes of the caller are complete
+  WtParams w;
+  wt_params(ctx, a, w);
+  if (ctx->math_mode == NOAHMP_MATH_PARITY) nmp_launch_wtable_parity(w, ctx->stream, &ctx->launches, 1);
+  else nmp_launch_wtable_fast(w, ctx->stream, &ctx->launches, 1);
+  const int T = 256;
+  wt_nonland_cells_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, ctx->stream>>>(
+      ctx->d_class, ctx->d_wt[WT_QRF], ctx->d_wt[WT_QSPRING], ctx->d_grid[F_rechxy], ctx->d_grid[F_deeprechxy], ctx->ncell);
+  ctx->launches++;
+  const int nother = (int)ctx->np - ctx->nclass[CL_LAND];
+  if (nother > 0) {
+    wt_nonland_cols_kernel<<<(nother + T - 1) / T, T, 0, ctx->stream>>>(ctx->d_state, ctx->np, ctx->nclass[CL_LAND], nother);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  if (ctx->sync_mode == NOAHMP_SYNC_FULL) return wt_download(ctx, a);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int noahmp_b200_wtable(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  int rc = noahmp_b200_wtable_begin(ctx, a);
+  if (rc) return rc;
+  return noahmp_b200_wtable_end(ctx, a);
+}
+
+int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  int rc = wt_check(ctx, a);
+  if (rc) return rc;
+  if (!ctx->d_kcell) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  return wt_download(ctx, a);
 }
 
 long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -146,6 +146,34 @@ class NoahMP:
             raise KeyError(field)
         return _DevArray(p, (n.value,), "<i4" if field in _capi.INT_ARRAYS else "<f4")
 
+    # ---- opt_run = 5 groundwater (WTABLE_mmf_noahmp) --------------------------------------------------
+    def wtable(self, arrays, scalars):
+        """CALL WTABLE_mmf_noahmp(...) on a tile that needs no halo (single tile = whole domain)."""
+        a = _capi.make_wtable_args(arrays, scalars)
+        self._check_rc(self._L.noahmp_b200_wtable(self._ctx, C.byref(a)))
+
+    def wtable_begin(self, arrays, scalars):
+        a = _capi.make_wtable_args(arrays, scalars)
+        self._check_rc(self._L.noahmp_b200_wtable_begin(self._ctx, C.byref(a)))
+
+    def wtable_end(self, arrays, scalars):
+        a = _capi.make_wtable_args(arrays, scalars)
+        self._check_rc(self._L.noahmp_b200_wtable_end(self._ctx, C.byref(a)))
+
+    def wtable_halo(self):
+        """(KCELL, HEAD) device planes of shape (nj+2, ni+2) with the one-cell halo ring."""
+        k, h = C.c_void_p(), C.c_void_p()
+        self._check_rc(self._L.noahmp_b200_wtable_halo(self._ctx, C.byref(k), C.byref(h)))
+        return _DevArray(k.value, (self.nj + 2, self.ni + 2)), _DevArray(h.value, (self.nj + 2, self.ni + 2))
+
+    def wtable_sync_host(self, arrays, scalars):
+        a = _capi.make_wtable_args(arrays, scalars)
+        self._check_rc(self._L.noahmp_b200_wtable_sync_host(self._ctx, C.byref(a)))
+
+    def _check_rc(self, rc):
+        if rc:
+            raise NoahmpError(rc, self._L.noahmp_b200_last_error().decode())
+
     # ---- bookkeeping -------------------------------------------------------------------------------
     @property
     def launches(self):

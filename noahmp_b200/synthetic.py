@@ -20,7 +20,8 @@ MASK32 = 0xFFFFFFFF
 
 # field ids for the hash
 (F_WATER, F_VEG, F_VEGSEL, F_SOIL, F_TMN, F_VEGFRA, F_HGT, F_SMOIS, F_SNOW, F_SNODEP,
- F_T, F_RH, F_U1, F_U2, F_V1, F_V2, F_GLW, F_SW, F_RAINP, F_RAINA) = range(20)
+ F_T, F_RH, F_U1, F_U2, F_V1, F_V2, F_GLW, F_SW, F_RAINP, F_RAINA, F_FDEPTH, F_EQWTD, F_RCOND, F_WTD0,
+ F_SMCWTD) = range(25)
 
 
 class _NP:
@@ -430,3 +431,44 @@ def args_from(cfg, st, frc, state, itimestep, nk=2):
               ids=1, ide=ni, jds=1, jde=nj, kds=1, kde=nk, ims=1, ime=ni, jms=1, jme=nj, kms=1, kme=nk,
               its=1, ite=ni, jts=1, jte=nj, kts=1, kte=nk)
     return arr, sc
+
+
+def _smooth_topo(cfg, g):
+    """Gently rolling terrain (slopes of a few m per km) as a function of the GLOBAL cell index: the lateral-flow
+    stencil needs a topography with physical gradients, unlike the white-noise HGT used for surface pressure."""
+    gi = (g % cfg.ni).astype(np.float64)
+    gj = (g // cfg.ni).astype(np.float64)
+    z = 400.0 + 60.0 * np.sin(2 * np.pi * gi / 97.0) * np.cos(2 * np.pi * gj / 131.0) + 25.0 * np.sin(2 * np.pi * (gi + 2 * gj) / 41.0)
+    return z.astype(np.float32)
+
+
+def groundwater_fields(cfg, st, state, dx=1000.0):
+    """Synthetic inputs of the opt_run=5 scheme for a tile, and MMF-consistent starting values
+    of the state GROUNDWATER_INIT (noahmpdrv.F90:1286-1470) would otherwise provide.  Returns (wt_arrays, scalars);
+    wt_arrays aliases state[...] for SMOIS, SH2O, SMCWTD, WTD (= ZWTXY), DEEPRECH, RECH so one dict serves both
+    noahmplsm and WTABLE."""
+    f = np.float32
+    g = st["_g"]
+    xp = backend()
+    u = lambda fld: uniform(xp, g, -1, fld)
+    nj, ni = g.shape
+    eq = (-20.0 + 19.0 * u(F_EQWTD)).astype(f)
+    A = {
+        "fdepth": (50.0 + 450.0 * u(F_FDEPTH)).astype(f), "area": np.full((nj, ni), dx * dx, f), "topo": _smooth_topo(cfg, g),
+        "rivercond": (1.0e-3 * u(F_RCOND)).astype(f), "riverbed": (eq - f(1.0)).astype(f), "eqwtd": eq,
+        "pexp": np.ones((nj, ni), f),
+        "qrf": np.zeros((nj, ni), f), "qspring": np.zeros((nj, ni), f), "qslat": np.zeros((nj, ni), f),
+        "qrfs": np.zeros((nj, ni), f), "qsprings": np.zeros((nj, ni), f),
+        "xland": st["xland"], "xice": st["xice"], "isltyp": st["isltyp"], "ivgtyp": st["ivgtyp"], "dzs": DZS,
+    }
+    state["zwtxy"][...] = (eq + (-3.0 + 6.0 * u(F_WTD0))).astype(f).clip(-40.0, -0.05)
+    state["smcwtdxy"][...] = (0.15 + 0.2 * u(F_SMCWTD)).astype(f)
+    state["smoiseq"][...] = (f(0.8) * state["smois"]).astype(f)
+    state["waxy"][...] = 0.0
+    for n, src in (("smois", "smois"), ("sh2oxy", "sh2o"), ("smcwtd", "smcwtdxy"), ("wtd", "zwtxy"),
+                   ("deeprech", "deeprechxy"), ("rech", "rechxy"), ("smoiseq", "smoiseq")):
+        A[n] = state[src]
+    sc = dict(nsoil=4, xice_threshold=0.5, isice=ISICE, isurban=ISURBAN, wtddt=30.0,
+              ids=1, ide=cfg.ni, jds=1, jde=cfg.nj, kds=1, kde=2, ims=1, ime=ni, jms=1, jme=nj, kms=1, kme=2,
+              its=1, ite=ni, jts=1, jte=nj, kts=1, kte=2)
+    return A, sc

@@ -37,6 +37,8 @@ def lib():
         _LIB.nmo_esat.argtypes = [C.c_float, C.POINTER(C.c_float)]
         _LIB.nmo_rosr12.argtypes = [C.c_int] + [C.c_void_p] * 5
         _LIB.nmo_combo.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.nmo_wtable.argtypes = [C.POINTER(_capi.NoahmpWtableArgs), C.POINTER(_capi.NoahmpTables)]
+        _LIB.nmo_wtable.restype = C.c_int
     return _LIB
 
 
@@ -67,3 +69,11 @@ def math_array(fn, x, y=None):
         yp = y.ctypes.data
     lib().nmo_math_array(fn, x.ctypes.data, yp, out.ctypes.data, x.size)
     return out
+
+
+def wtable(arrays, scalars, tables_struct):
+    """One call of the oracle's WTABLE_mmf_noahmp on host arrays (updated in place)."""
+    a = _capi.make_wtable_args(arrays, scalars)
+    rc = lib().nmo_wtable(C.byref(a), C.byref(tables_struct))
+    if rc:
+        raise RuntimeError(f"nmo_wtable failed: {rc}")

@@ -299,3 +299,56 @@ def test_full_size_properties_conus(built, tables_usgs):
     for n in ("tsk", "snow", "isnowxy", "hfx", "lh", "xlaixy"):
         assert np.array_equal(small[n], big[n][wy:wy + 48, wx:wx + 64]), n
     assert np.array_equal(small["tslb"], big["tslb"][wy:wy + 48, :, wx:wx + 64])
+
+
+# ---- opt_run = 5: WTABLE_mmf_noahmp on the device ------------------------------------------------------------------
+def _gw_case(tables, ni, nj):
+    cfg = _cfg("C4", ni, nj, iopt_run=5)
+    _, st, state = make_case(cfg, tables)
+    wt, wsc = S.groundwater_fields(cfg, st, state)
+    return cfg, st, state, wt, wsc
+
+
+WT_FIELDS = ["smois", "sh2oxy", "smcwtd", "wtd", "deeprech", "rech", "qrf", "qspring", "qslat", "qrfs", "qsprings"]
+
+
+def _clone_gw(state, wt):
+    s2 = clone_state(state)
+    w2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in wt.items()}
+    for n, src in (("smois", "smois"), ("sh2oxy", "sh2o"), ("smcwtd", "smcwtdxy"), ("wtd", "zwtxy"),
+                   ("deeprech", "deeprechxy"), ("rech", "rechxy"), ("smoiseq", "smoiseq")):
+        w2[n] = s2[src]
+    return s2, w2
+
+
+@pytest.mark.parametrize("sync", [0, 1])
+def test_groundwater_step_bitexact(built, tables_usgs, sync):
+    """noahmplsm(opt_run=5) + WTABLE_mmf_noahmp every step, 12 steps, land/water/glacier tile: the PARITY build equals
+    the oracle bit for bit — in strict drop-in mode and with the state resident in HBM."""
+    import noahmp_b200
+    from oracle import oracle as O
+    cfg, st, state, wt, wsc = _gw_case(tables_usgs, 72, 56)
+    ts = _capi.tables_from_dict(tables_usgs)
+    s_cpu, w_cpu = _clone_gw(state, wt)
+    s_gpu, w_gpu = _clone_gw(state, wt)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY, sync=sync)
+    xp = S.backend()
+    O.set_math_mode(1)
+    for step in range(1, 13):
+        frc = S.forcing(xp, cfg, step, st)
+        a1, sc = S.args_from(cfg, st, frc, s_cpu, step)
+        a2, _ = S.args_from(cfg, st, frc, s_gpu, step)
+        e1, _ = O.noahmplsm(a1, sc, ts, nthreads=4)
+        e2 = m.noahmplsm(a2, sc)
+        assert (e1.code, e1.count) == (e2.code, e2.count) == (0, 0), (step, e1.code, e2.code)
+        O.wtable(w_cpu, wsc, ts)
+        m.wtable(w_gpu, wsc)
+    if sync == 1:
+        m.sync_host(a2, sc)
+        m.wtable_sync_host(w_gpu, wsc)
+    rep = diff_report(s_cpu, s_gpu)
+    assert not rep, rep
+    for n in WT_FIELDS:
+        assert np.array_equal(w_cpu[n].view(np.int32), w_gpu[n].view(np.int32)), n
+    assert np.abs(w_gpu["qslat"]).max() > 0 and w_gpu["qrfs"].max() > 0
+    m.close()
