@@ -32,6 +32,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_COLUMN_STEP = 824  # 87 words read + 119 words written at the noahmplsm boundary
+# from the ncu --set full capture of the CONUS launch (profiles/r01_ncu_land_conus_summary.txt): DRAM bytes moved and
+# warp-instructions executed per column by land_kernel<dynveg>
+NCU_DRAM_BYTES_PER_COLUMN = (13.583711e9 + 23.223140e9) / 17694720
+NCU_WARP_INSTR_PER_COLUMN = 9276089410 / 17694720
+N_SM, SCHED_PER_SM = 148, 4
 FORCING_ORDER = ["coszin", "t", "qv", "u", "v", "swdown", "glw", "p", "p", "rainbl", "vegfra", "dz8w"]
 
 
@@ -337,11 +342,21 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": f"land_kernel<{model.variant}>",
+                         "traffic": NCU_DRAM_BYTES_PER_COLUMN * ncol if cfg.name == "C3" else None,
+                         "traffic_source": "ncu dram__bytes_read+write of the CONUS launch, profiles/r01_ncu_land_conus_summary.txt",
+                         "peak_source": peak_src, "kernel": f"land_kernel<{model.variant}>",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLUMN_STEP,
                          "columns_per_launch": ncol, "kernel_ms": mean_ms,
                          "note": "step = memset x2 + land_kernel (+glacier/sea-ice kernels when present); "
                                  "the physics is FP32/SFU-issue bound, see DESIGN.md"},
+            # the binding resource: warp-instruction issue slots (FP32 / SFU pipes), not HBM
+            "issue_roofline": {"bound": "fp32/sfu issue", "warp_instr_per_column": NCU_WARP_INSTR_PER_COLUMN,
+                               "achieved_warp_instr_per_s": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3),
+                               "peak_warp_instr_per_s": N_SM * SCHED_PER_SM * (clocks["sm_mhz"] or 1965.0) * 1e6,
+                               "frac": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3)
+                                       / (N_SM * SCHED_PER_SM * (clocks["sm_mhz"] or 1965.0) * 1e6),
+                               "simt_efficiency": 0.546,
+                               "source": "instruction count from ncu (profiles/), time and clock measured live"},
             "clocks": clocks, "gpu_launches": launches_all, "census": census, "math": args.math,
         }
         if e2e:

@@ -32,6 +32,11 @@
 #ifndef NMP_PHASE_SYNC
 #define NMP_PHASE_SYNC 0
 #endif
+// NMP_SORT: land_kernel assigns the columns of a block to its threads sorted by (snow-layer count, canopy Newton
+// passes of the previous step), so that the lanes of a warp take the same branches and leave loops together.
+#ifndef NMP_SORT
+#define NMP_SORT 0
+#endif
 // NMP_PHASE_SYNC: 0 = no barriers, 1 = barriers between all ~16 phases, 2 = only between the major phases
 #if NMP_PHASE_SYNC == 1
 #define NMP_PHASE() __syncthreads()

@@ -60,6 +60,10 @@ struct SlotTable {
 };
 constexpr SlotTable kSlots{};
 constexpr int NPLANES = kSlots.slot[NFIELDS];
+// internal planes after the argument-list fields: [NPLANES] = VEGE_FLUX pass count of the previous step (the
+// key of the in-block column sort of land_kernel)
+constexpr int PLANE_PREV_ITERS = NPLANES;
+constexpr int NPLANES_ALLOC = NPLANES + 1;
 template <int F>
 struct SlotOf {
   static constexpr int value = kSlots.slot[F];

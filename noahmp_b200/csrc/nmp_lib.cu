@@ -371,7 +371,9 @@ static int classify(noahmp_b200_ctx* ctx) {
   ctx->nclass[CL_WATER] = (int)(nc - offset);
   if (ctx->np > ctx->np_alloc) {
     if (ctx->d_state) CK(cudaFree(ctx->d_state));
-    CK(cudaMalloc(&ctx->d_state, sizeof(float) * (size_t)NPLANES * (size_t)ctx->np));
+    CK(cudaMalloc(&ctx->d_state, sizeof(float) * (size_t)NPLANES_ALLOC * (size_t)ctx->np));
+    CK(cudaMemsetAsync(ctx->d_state + (size_t)PLANE_PREV_ITERS * (size_t)ctx->np, 0, sizeof(float) * (size_t)ctx->np,
+                       ctx->stream));
     ctx->np_alloc = ctx->np;
   }
   ctx->h_cell.resize((size_t)ctx->np);
