@@ -92,3 +92,10 @@ print("SIMT efficiency (predicated-on threads / 32) of the heaviest functions:")
 for k, v in we.most_common(16):
     print("  %-20s %.2f" % (k, te[k] / (32.0 * v)))
 print("  overall %.3f" % (sum(te.values()) / (32.0 * sum(we.values()))))
+# where the long-scoreboard and barrier stalls are
+for stall in ("stall_long_sb", "stall_barrier", "stall_wait"):
+    byf = collections.Counter()
+    for i, r in enumerate(data):
+        byf[fn(ins[i])] += int(r[ix[stall]])
+    tot_s = sum(byf.values()) or 1
+    print(stall, "by function:", ", ".join(f"{k} {v / tot_s:.2f}" for k, v in byf.most_common(10)))
