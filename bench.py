@@ -32,10 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_COLUMN_STEP = 824  # 87 words read + 119 words written at the noahmplsm boundary
-# from the ncu --set full capture of the CONUS launch (profiles/r01_ncu_land_conus_summary.txt): DRAM bytes moved and
+# from the ncu --set full capture of the CONUS launch (profiles/r01_ncu_land_conus_v5_summary.txt): DRAM bytes moved and
 # warp-instructions executed per column by land_kernel<dynveg>
-NCU_DRAM_BYTES_PER_COLUMN = (13.583711e9 + 23.223140e9) / 17694720
-NCU_WARP_INSTR_PER_COLUMN = 9276089410 / 17694720
+NCU_DRAM_BYTES_PER_COLUMN = (5.375662e9 + 11.196308e9) / 17694720
+NCU_WARP_INSTR_PER_COLUMN = 5816728843 / 17694720
 N_SM, SCHED_PER_SM = 148, 4
 FORCING_ORDER = ["coszin", "t", "qv", "u", "v", "swdown", "glw", "p", "p", "rainbl", "vegfra", "dz8w"]
 
@@ -343,7 +343,7 @@ def main():
             "config": workload_config(cfg, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_COLUMN * ncol if cfg.name == "C3" else None,
-                         "traffic_source": "ncu dram__bytes_read+write of the CONUS launch, profiles/r01_ncu_land_conus_summary.txt",
+                         "traffic_source": "ncu dram__bytes_read+write of the CONUS launch, profiles/r01_ncu_land_conus_v5_summary.txt",
                          "peak_source": peak_src, "kernel": f"land_kernel<{model.variant}>",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLUMN_STEP,
                          "columns_per_launch": ncol, "kernel_ms": mean_ms,
@@ -355,7 +355,7 @@ def main():
                                "peak_warp_instr_per_s": N_SM * SCHED_PER_SM * (clocks["sm_mhz"] or 1965.0) * 1e6,
                                "frac": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3)
                                        / (N_SM * SCHED_PER_SM * (clocks["sm_mhz"] or 1965.0) * 1e6),
-                               "simt_efficiency": 0.546,
+                               "simt_efficiency": 0.647,
                                "source": "instruction count from ncu (profiles/), time and clock measured live"},
             "clocks": clocks, "gpu_launches": launches_all, "census": census, "math": args.math,
         }
