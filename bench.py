@@ -173,7 +173,9 @@ def run_reference(args):
 
 
 def workload_config(cfg, n):
-    return {"workload": f"{cfg.name}: CONUS 1 km {cfg.ni}x{cfg.nj} hourly NoahMP step, dveg={cfg.opts['idveg']} "
+    title = {"C3": "CONUS 1 km", "C4": "global 0.05 deg land mask incl. glacier", "C2": "NLDAS 0.125 deg",
+             "C1": "HRLDAS 10x10"}.get(cfg.name, cfg.name)
+    return {"workload": f"{cfg.name}: {title} {cfg.ni}x{cfg.nj} hourly NoahMP step, dveg={cfg.opts['idveg']} "
                         f"opt_run={cfg.opts['iopt_run']}, {int(cfg.snow_frac * 100)}% columns with 3-layer snow",
             "grid": [cfg.ni, cfg.nj], "tiling": f"mpp_land_partition {n} rank(s)",
             "l2": "inputs larger than L2 (state+forcing per rank >> 126 MB); no flush needed",
