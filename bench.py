@@ -338,6 +338,11 @@ def main():
         # dominant kernel = land_kernel: the timed region is (memsets +) land kernel per step on this rank
         mean_ms = float(np.mean(step_ms))
         achieved = ALG_BYTES_PER_COLUMN_STEP * ncol / (mean_ms * 1e-3) / 1e9
+        try:  # measured FP32 issue peak of this GPU type (thread-instructions/s -> warp-instructions/s)
+            with open(os.path.join(ROOT, "profiles", "r01_peaks.json")) as f:
+                issue_peak, measured_issue = json.load(f)["ffma_thread_instr_per_s"] / 32.0, True
+        except Exception:
+            issue_peak, measured_issue = N_SM * SCHED_PER_SM * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6, False
         line = {
             "metric": "column-timesteps/sec", "value": value, "unit": "column-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -354,9 +359,10 @@ def main():
             # the binding resource: warp-instruction issue slots (FP32 / SFU pipes), not HBM
             "issue_roofline": {"bound": "fp32/sfu issue", "warp_instr_per_column": NCU_WARP_INSTR_PER_COLUMN,
                                "achieved_warp_instr_per_s": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3),
-                               "peak_warp_instr_per_s": N_SM * SCHED_PER_SM * (clocks["sm_mhz"] or 1965.0) * 1e6,
-                               "frac": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3)
-                                       / (N_SM * SCHED_PER_SM * (clocks["sm_mhz"] or 1965.0) * 1e6),
+                               "peak_warp_instr_per_s": issue_peak,
+                               "peak_source": "measured FFMA issue rate, tools/peaks.cu -> profiles/r01_peaks.json"
+                                              if measured_issue else "nominal 148 SM x 4 schedulers x SM clock",
+                               "frac": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3) / issue_peak,
                                "simt_efficiency": 0.647,
                                "source": "instruction count from ncu (profiles/), time and clock measured live"},
             "clocks": clocks, "gpu_launches": launches_all, "census": census, "math": args.math,

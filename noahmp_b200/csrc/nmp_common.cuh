@@ -48,6 +48,13 @@
 #define NMP_PHASE() ((void)0)
 #define NMP_PHASE_MAJOR() ((void)0)
 #endif
+// barriers A (after the canopy loop) and B (after the ground loop) can be dropped separately (tuning sweeps)
+#ifndef NMP_SYNC_AFTER_VEGE
+#define NMP_SYNC_AFTER_VEGE 1
+#endif
+#ifndef NMP_SYNC_AFTER_BARE
+#define NMP_SYNC_AFTER_BARE 1
+#endif
 
 #define NMP_DEV __device__ __forceinline__
 #define NMP_DEVN __device__ __noinline__
