@@ -321,13 +321,52 @@ def main():
             raise SystemExit(f"e2e: model check failed code {stt.code}")
         e2e = (e2e_s, h2d, d2h)
 
+    # ---- e2e through the on-device forcing pipeline (row f2): forcing FILES every 3 h, interpolation on the GPU ------
+    e2e_f2 = None
+    if not args.no_e2e:
+        idx = {n: i for i, n in enumerate(FORCING_ORDER)}
+        files = []
+        for h in range(R):
+            f = ring[h]
+            d = {"t": f[idx["t"]], "q": f[idx["qv"]], "u": f[idx["u"]], "v": f[idx["v"]], "p": f[7], "lw": f[idx["glw"]],
+                 "sw": f[idx["swdown"]], "pcp": f[idx["rainbl"]] / float(cfg.dt), "fpar": f[idx["vegfra"]] / 100.0}
+            files.append({n: t.float().cpu().pin_memory().numpy() for n, t in d.items()})
+        model.forcing_static(st["xlatin"], st["xlong"], 30.0)
+        model.forcing_upload(0, files[0]); model.forcing_upload(1, files[1])
+        nfile = 1
+
+        def f2_step(k, count):
+            nonlocal nfile
+            sub = count % 3
+            if sub == 0 and count > 0:  # the model time reached file B
+                model.forcing_swap()
+                nfile += 1
+                model.forcing_upload(1, files[nfile % R])  # asynchronous; overlaps the steps below
+            yr, julian, hour = S.clock(cfg, 1 + k)
+            jul = model.forcing_apply(float(np.float32(3 - sub) / np.float32(3)), int(julian), int(hour), 0, 0, float(cfg.dt))
+            s2 = dict(sc)
+            s2.update(itimestep=1 + k, yr=yr, julian=jul)
+            return model.noahmplsm_device_forcing(e_arr, s2)
+
+        cnt = 0
+        for _ in range(3):
+            f2_step(k, cnt); k += 1; cnt += 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            stt = f2_step(k, cnt); k += 1; cnt += 1
+        barrier()
+        e2e_f2 = time.perf_counter() - t0
+        if stt.code:
+            raise SystemExit(f"e2e (forcing pipeline): model check failed code {stt.code}")
+
     # ---- reduce over ranks ---------------------------------------------------------------------------------
-    vals = torch.tensor([total_ms, float(ncol), e2e[0] if e2e else 0.0, float(gpu_launches)], device=dev,
+    vals = torch.tensor([total_ms, float(ncol), e2e[0] if e2e else 0.0, float(gpu_launches), e2e_f2 or 0.0], device=dev,
                         dtype=torch.float64)
     if world > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, e2e_s_max = float(mx[0]), float(mx[2])
+        total_ms, e2e_s_max, e2e_f2 = float(mx[0]), float(mx[2]), float(mx[4])
         ncol_all, launches_all = float(sm[1]), int(sm[3])
     else:
         e2e_s_max, ncol_all, launches_all = (e2e[0] if e2e else 0.0), float(ncol), int(gpu_launches)
@@ -372,6 +411,11 @@ def main():
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
                            "call": "noahmp_b200_noahmplsm (RESIDENT state, set_fetch=tsk,hfx,lh,grdflx; 8 row chunks), pinned host buffers",
                            "ms_per_step": 1e3 * e2e_s_max / args.steps}
+            line["e2e_forcing_pipeline"] = {
+                "value": ncol_all * args.steps / e2e_f2, "unit": "column-steps/s", "ms_per_step": 1e3 * e2e_f2 / args.steps,
+                "h2d_bytes_per_step": 9 * 4 * ni * nj // 3, "d2h_bytes_per_step": e2e[2],
+                "call": "row f2: noahmp_b200_forcing_upload (9 file fields every 3 steps, async) + forcing_apply + "
+                        "noahmplsm_device_forcing (same fetch list)"}
         else:
             line["e2e"] = None
         if world == 1 and not args.no_cpu_baseline:

@@ -239,6 +239,31 @@ float* noahmp_b200_device_state(noahmp_b200_ctx* ctx, const char* field, int lay
 int noahmp_b200_enable_iteration_counts(noahmp_b200_ctx* ctx, int enable);
 int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out);
 
+/* ---- forcing pipeline on the device -----------------------------------------------------
+ * Replaces, for a driver that hands the raw forcing-file fields to the library at INPUT cadence instead of
+ * interpolated arrays at every step:
+ *   hrldas_input_interpolate / hrldas_input_copy   driver/module_hrldas_netcdf_io.F90:1351-1404
+ *   VEGFRA*100, level-2 copies, RAINBL = rate*dt, DZ8W = 2*zlvl        module_hrldas_noahmp_driver.F90:336-344
+ *   the CALC_DECLIN loop (COSZEN, JULIAN)                              module_hrldas_noahmp_driver.F90:350-354, :813-863
+ * The interpolated planes never exist on the host; per step nothing crosses PCIe but the fetch list. */
+typedef struct noahmp_forcing_fields {
+  /* one forcing file (xstart:xend, ystart:yend): T2D Q2D U2D V2D PSFC LWDOWN SWDOWN RAINRATE, VEGFRA as fraction */
+  const float *t, *q, *u, *v, *p, *lw, *sw, *pcp, *fpar;
+} noahmp_forcing_fields;
+/* lat2d / lon2d in degrees (the CALC_DECLIN arguments), zlvl = config%zlvl (30 m). */
+int noahmp_b200_forcing_static(noahmp_b200_ctx* ctx, const float* lat2d, const float* lon2d, float zlvl);
+/* Asynchronous upload of one bracket: slot 0 = instructA (earlier file), 1 = instructB (later file). */
+int noahmp_b200_forcing_upload(noahmp_b200_ctx* ctx, int slot, const noahmp_forcing_fields* fields);
+/* instructB becomes instructA (the model time passed the later file). */
+int noahmp_b200_forcing_swap(noahmp_b200_ctx* ctx);
+/* Fill the device forcing planes for one model step: fraction = real(idts2-idts)/real(idts2) (1 = exactly at A,
+ * which is hrldas_input_copy); date parts of the step's NOWDATE; returns JULIAN through *julian. */
+int noahmp_b200_forcing_apply(noahmp_b200_ctx* ctx, float fraction, int iday, int ihour, int iminute, int isecond,
+                              float model_timestep, float* julian);
+/* noahmp_b200_noahmplsm for a context whose forcing planes were filled by noahmp_b200_forcing_apply: the forcing
+ * pointers of `args` are ignored (may be NULL); RESIDENT mode only; same row-chunk pipeline and fetch list. */
+int noahmp_b200_noahmplsm_device_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, noahmp_status* status);
+
 /* ---- opt_run = 5: Miguez-Macho & Fan groundwater, replaces `CALL WTABLE_mmf_noahmp(...)` ----------------------
  * phys/module_sf_noahmp_groundwater.F90:14-198 (LATERALFLOW :201-295, UPDATEWTD :298-606), called by
  * land_driver_exe every STEPWTD steps (driver/module_hrldas_noahmp_driver.F90:420-436).  One member per dummy

@@ -173,3 +173,21 @@ def make_wtable_args(arrays, scalars):
                 raise TypeError(f"{n}: need C-contiguous {want.__name__}, got {arr.dtype}")
             setattr(a, n, arr.ctypes.data_as(_K[k]))
     return a
+
+
+# ---- on-device forcing pipeline (row f2): noahmp_forcing_fields ---------------------------------------------------
+FORCING_FIELDS = "t q u v p lw sw pcp fpar".split()
+
+
+class NoahmpForcingFields(C.Structure):
+    _fields_ = [(n, _pf) for n in FORCING_FIELDS]
+
+
+def make_forcing_fields(d):
+    f = NoahmpForcingFields()
+    for n in FORCING_FIELDS:
+        arr = d[n]
+        if arr.dtype != np.float32 or not arr.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{n}: need C-contiguous float32")
+        setattr(f, n, arr.ctypes.data_as(_pf))
+    return f

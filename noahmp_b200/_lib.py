@@ -18,6 +18,7 @@ _pa = C.POINTER(_capi.NoahmpLsmArgs)
 _pt = C.POINTER(_capi.NoahmpTables)
 _ps = C.POINTER(_capi.NoahmpStatus)
 _pw = C.POINTER(_capi.NoahmpWtableArgs)
+_pff = C.POINTER(_capi.NoahmpForcingFields)
 _ctx = C.c_void_p
 
 # name -> (restype, argtypes); every symbol include/noahmp_b200.h declares
@@ -48,6 +49,12 @@ SYMBOLS = {
     "noahmp_b200_device_state": (C.c_void_p, [_ctx, C.c_char_p, C.c_int, C.POINTER(C.c_longlong)]),
     "noahmp_b200_enable_iteration_counts": (C.c_int, [_ctx, C.c_int]),
     "noahmp_b200_get_iteration_counts": (C.c_int, [_ctx, C.POINTER(C.c_int32)]),
+    "noahmp_b200_forcing_static": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_float]),
+    "noahmp_b200_forcing_upload": (C.c_int, [_ctx, C.c_int, _pff]),
+    "noahmp_b200_forcing_swap": (C.c_int, [_ctx]),
+    "noahmp_b200_forcing_apply": (C.c_int, [_ctx, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                           C.POINTER(C.c_float)]),
+    "noahmp_b200_noahmplsm_device_forcing": (C.c_int, [_ctx, _pa, _ps]),
     "noahmp_b200_wtable": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_wtable_begin": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_wtable_end": (C.c_int, [_ctx, _pw]),

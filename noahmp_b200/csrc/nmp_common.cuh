@@ -79,6 +79,7 @@ NMP_DEV double DPOW(double x, double y) { return nmpm::pow_d(x, y); }
 NMP_DEV float ATAN(float x) { return nmpm::atanf_(x); }
 NMP_DEV float TAN(float x) { return nmpm::tanf_(x); }
 NMP_DEV float COS(float x) { return nmpm::cosf_(x); }
+NMP_DEV float SIN(float x) { return nmpm::sinf_(x); }
 NMP_DEV float ACOS(float x) { return nmpm::acosf_(x); }
 NMP_DEV float TANH(float x) { return nmpm::tanhf_(x); }
 NMP_DEV float SQRT(float x) { return __fsqrt_rn(x); }
@@ -96,6 +97,7 @@ NMP_DEV double DPOW(double x, double y) { return pow(x, y); }
 NMP_DEV float ATAN(float x) { return atanf(x); }
 NMP_DEV float TAN(float x) { return tanf(x); }
 NMP_DEV float COS(float x) { return cosf(x); }
+NMP_DEV float SIN(float x) { return sinf(x); }
 NMP_DEV float ACOS(float x) { return acosf(x); }
 NMP_DEV float TANH(float x) { return tanhf(x); }
 NMP_DEV float SQRT(float x) { return sqrtf(x); }
@@ -109,6 +111,7 @@ NMP_DEV double DPOW(double x, double y) { return pow(x, y); }
 NMP_DEV float ATAN(float x) { return atanf(x); }
 NMP_DEV float TAN(float x) { return tanf(x); }
 NMP_DEV float COS(float x) { return cosf(x); }
+NMP_DEV float SIN(float x) { return sinf(x); }
 NMP_DEV float ACOS(float x) { return acosf(x); }
 NMP_DEV float TANH(float x) { return tanhf(x); }
 NMP_DEV float SQRT(float x) { return sqrtf(x); }

@@ -118,6 +118,16 @@ struct WtParams {
   float dzs[NOAHMP_NSOIL];
 };
 
+// kernel parameter block of the on-device forcing pipeline (nmp_forcing.cuh)
+struct ForcingParams {
+  const float* A[9];  // t q u v p lw sw pcp fpar of the earlier bracket
+  const float* B[9];  // ... of the later bracket (only t..sw are read)
+  const float *lat, *lon;
+  float* out[NFORC];
+  long long ncell;
+  float fraction, sin_declin, cos_declin, hour_frac /* IHOUR + IMINUTE/60 + ISECOND/3600 */, dt, zlvl;
+};
+
 // compact-column ranges one launch of the physics covers (a whole tile, or one row chunk of it)
 struct StepRange {
   int land_first, land_count, glac_first, glac_count;

@@ -2,6 +2,7 @@
 #define NMP_PARITY 0
 #include "nmp_kernels.cuh"
 #include "nmp_groundwater.cuh"
+#include "nmp_forcing.cuh"
 
 const char* nmp_launch_step_fast(const nmpf::StepParams& base, const nmpf::StepRange& r, cudaStream_t stream,
                                      long long* launches) {
@@ -10,4 +11,8 @@ const char* nmp_launch_step_fast(const nmpf::StepParams& base, const nmpf::StepR
 
 void nmp_launch_wtable_fast(const nmpf::WtParams& w, cudaStream_t stream, long long* launches, int phase) {
   launch_wtable(w, stream, launches, phase);
+}
+
+void nmp_launch_forcing_fast(const nmpf::ForcingParams& f, cudaStream_t stream, long long* launches) {
+  launch_forcing(f, stream, launches);
 }

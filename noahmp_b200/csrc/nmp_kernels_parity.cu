@@ -4,6 +4,7 @@
 #define NMP_PARITY 1
 #include "nmp_kernels.cuh"
 #include "nmp_groundwater.cuh"
+#include "nmp_forcing.cuh"
 
 const char* nmp_launch_step_parity(const nmpf::StepParams& base, const nmpf::StepRange& r, cudaStream_t stream,
                                        long long* launches) {
@@ -12,4 +13,8 @@ const char* nmp_launch_step_parity(const nmpf::StepParams& base, const nmpf::Ste
 
 void nmp_launch_wtable_parity(const nmpf::WtParams& w, cudaStream_t stream, long long* launches, int phase) {
   launch_wtable(w, stream, launches, phase);
+}
+
+void nmp_launch_forcing_parity(const nmpf::ForcingParams& f, cudaStream_t stream, long long* launches) {
+  launch_forcing(f, stream, launches);
 }

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "nmp_fields.h"
+#include "nmp_math.h"
 
 using namespace nmpf;
 
@@ -25,6 +26,8 @@ const char* nmp_launch_step_fast(const StepParams& base, const StepRange& r, cud
 const char* nmp_launch_step_parity(const StepParams& base, const StepRange& r, cudaStream_t stream, long long* launches);
 void nmp_launch_wtable_fast(const WtParams& w, cudaStream_t stream, long long* launches, int phase);
 void nmp_launch_wtable_parity(const WtParams& w, cudaStream_t stream, long long* launches, int phase);
+void nmp_launch_forcing_fast(const ForcingParams& f, cudaStream_t stream, long long* launches);
+void nmp_launch_forcing_parity(const ForcingParams& f, cudaStream_t stream, long long* launches);
 
 static thread_local std::string g_last_error;
 static void set_error(const std::string& s) { g_last_error = s; }
@@ -102,6 +105,12 @@ struct noahmp_b200_ctx {
   float* d_wt[12] = {};
   float *d_kcell = nullptr, *d_head = nullptr;
   bool wt_init = false;
+  // on-device forcing pipeline (row f2): two brackets of 9 planes, lat / lon
+  float* d_fb[2][9] = {};
+  float *d_lat = nullptr, *d_lon = nullptr;
+  float zlvl = 30.f;
+  cudaEvent_t ev_fb[2] = {};
+  bool fb_static = false, fb_loaded[2] = {false, false};
 };
 
 // ---- small kernels ------------------------------------------------------------------------------------
@@ -516,6 +525,9 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   cudaFree(ctx->d_state); cudaFree(ctx->d_planes); cudaFree(ctx->d_cell); cudaFree(ctx->d_class);
   cudaFree(ctx->d_cub); cudaFree(ctx->d_nsel); cudaFree(ctx->d_errkey); cudaFree(ctx->d_errcount);
   cudaFree(ctx->d_vege_iters);
+  for (auto& b : ctx->d_fb) for (auto p : b) cudaFree(p);
+  cudaFree(ctx->d_lat); cudaFree(ctx->d_lon);
+  for (auto e : ctx->ev_fb) if (e) cudaEventDestroy(e);
   for (auto p : ctx->d_wt) cudaFree(p);
   cudaFree(ctx->d_kcell); cudaFree(ctx->d_head);
   if (ctx->h_errkey) cudaFreeHost(ctx->h_errkey);
@@ -656,7 +668,7 @@ static int h2d_rows(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, 
 // RESIDENT-mode step as a row-chunk pipeline: while chunk c is computed, the forcing rows of chunk c+1 are on
 // their way up and the requested result fields of chunk c-1 on their way down (three streams, events in between).
 // Columns of a class are stored in grid order, so a row chunk is one contiguous compact range per class.
-static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, int nchunks) {
+static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, int nchunks, bool upload = true) {
   const int nk = a->kme - a->kms + 1, kms = a->kms, ni = ctx->ni, nj = ctx->nj;
   if (!ctx->s_in) {
     CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -674,7 +686,8 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
       {FC_COSZIN, a->coszin, 1, 1}, {FC_T, a->t3d, nk, 1},       {FC_QV, a->qv3d, nk, 1},      {FC_U, a->u_phy, nk, 1},
       {FC_V, a->v_phy, nk, 1},      {FC_SWDOWN, a->swdown, 1, 1}, {FC_GLW, a->glw, 1, 1},      {FC_P1, a->p8w3d, nk, a->kts},
       {FC_P2, a->p8w3d, nk, a->kts + 1}, {FC_RAINBL, a->rainbl, 1, 1}, {FC_VEGFRA, a->vegfra, 1, 1}, {FC_DZ8W, a->dz8w, nk, 1}};
-  for (const Plane& pl : planes) pin(ctx, pl.src, sizeof(float) * (size_t)ni * nj * pl.nk);
+  if (upload)
+    for (const Plane& pl : planes) pin(ctx, pl.src, sizeof(float) * (size_t)ni * nj * pl.nk);
   for (int f : ctx->fetch) pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
 
   StepParams p = ctx->base;
@@ -700,12 +713,14 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
   for (int c = 0; c < nchunks; ++c) {
     const int j0 = (int)((long long)nj * c / nchunks), j1 = (int)((long long)nj * (c + 1) / nchunks);
     if (j1 <= j0) continue;
-    for (const Plane& pl : planes) {
-      int rc = h2d_rows(ctx, ctx->d_forc[pl.id], pl.src, pl.nk, kms, pl.lev, j0, j1, ctx->s_in);
-      if (rc) return rc;
+    if (upload) {
+      for (const Plane& pl : planes) {
+        int rc = h2d_rows(ctx, ctx->d_forc[pl.id], pl.src, pl.nk, kms, pl.lev, j0, j1, ctx->s_in);
+        if (rc) return rc;
+      }
+      CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+      CK(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
     }
-    CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
-    CK(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
     const int c0 = j0 * ni, c1 = j1 * ni;
     StepRange r;
     r.land_first = lower(0, nland, c0);
@@ -1045,6 +1060,129 @@ int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args*
   CK(cudaSetDevice(ctx->device));
   CK(cudaDeviceSynchronize());
   return wt_download(ctx, a);
+}
+
+// ---- on-device forcing pipeline (row f2) ------------------------------------------------------------------------
+static int fb_alloc(noahmp_b200_ctx* ctx) {
+  if (ctx->d_lat) return 0;
+  const size_t plane = sizeof(float) * ctx->ncell;
+  for (auto& b : ctx->d_fb)
+    for (auto& p : b) { CK(cudaMalloc(&p, plane)); CK(cudaMemsetAsync(p, 0, plane, ctx->stream)); }
+  CK(cudaMalloc(&ctx->d_lat, plane));
+  CK(cudaMalloc(&ctx->d_lon, plane));
+  for (auto& e : ctx->ev_fb) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (!ctx->s_in) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int noahmp_b200_forcing_static(noahmp_b200_ctx* ctx, const float* lat2d, const float* lon2d, float zlvl) {
+  if (!ctx || !lat2d || !lon2d) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = fb_alloc(ctx);
+  if (rc) return rc;
+  const size_t plane = sizeof(float) * ctx->ncell;
+  CK(cudaMemcpyAsync(ctx->d_lat, lat2d, plane, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_lon, lon2d, plane, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->zlvl = zlvl;
+  ctx->fb_static = true;
+  return 0;
+}
+
+int noahmp_b200_forcing_upload(noahmp_b200_ctx* ctx, int slot, const noahmp_forcing_fields* f) {
+  if (!ctx || !f || slot < 0 || slot > 1) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = fb_alloc(ctx);
+  if (rc) return rc;
+  const float* src[9] = {f->t, f->q, f->u, f->v, f->p, f->lw, f->sw, f->pcp, f->fpar};
+  const size_t plane = sizeof(float) * ctx->ncell;
+  // the physics may still be reading planes derived from this slot: order the copy after the compute stream
+  CK(cudaEventRecord(ctx->ev_fb[slot], ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_fb[slot], 0));
+  for (int k = 0; k < 9; ++k) {
+    if (!src[k]) { set_error("forcing_upload: null field"); return NOAHMP_ERR_ARG; }
+    pin(ctx, src[k], plane);
+    CK(cudaMemcpyAsync(ctx->d_fb[slot][k], src[k], plane, cudaMemcpyHostToDevice, ctx->s_in));
+  }
+  CK(cudaEventRecord(ctx->ev_fb[slot], ctx->s_in));
+  ctx->fb_loaded[slot] = true;
+  return 0;
+}
+
+int noahmp_b200_forcing_swap(noahmp_b200_ctx* ctx) {
+  if (!ctx) return NOAHMP_ERR_ARG;
+  for (int k = 0; k < 9; ++k) std::swap(ctx->d_fb[0][k], ctx->d_fb[1][k]);
+  std::swap(ctx->ev_fb[0], ctx->ev_fb[1]);
+  std::swap(ctx->fb_loaded[0], ctx->fb_loaded[1]);
+  return 0;
+}
+
+int noahmp_b200_forcing_apply(noahmp_b200_ctx* ctx, float fraction, int iday, int ihour, int iminute, int isecond,
+                              float model_timestep, float* julian_out) {
+  if (!ctx || !ctx->fb_static || !ctx->fb_loaded[0]) { set_error("forcing_apply before forcing_static / forcing_upload"); return NOAHMP_ERR_ARG; }
+  if (fraction != 1.0f && !ctx->fb_loaded[1]) { set_error("forcing_apply: bracket B not loaded"); return NOAHMP_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const bool parity = ctx->math_mode == NOAHMP_MATH_PARITY;
+  auto fsin = [&](float x) { return parity ? nmpm::sinf_(x) : sinf(x); };
+  auto fcos = [&](float x) { return parity ? nmpm::cosf_(x) : cosf(x); };
+  auto fasin = [&](float x) { return parity ? nmpm::asinf_(x) : asinf(x); };
+  // CALC_DECLIN, the part that does not depend on the cell (:833-850)
+  const float DEGRAD = 3.14159265f / 180.f, DPD = 360.f / 365.f;
+  const float JULIAN = (float)iday + (float)ihour / 24.f;
+  const float OBECL = 23.5f * DEGRAD;
+  const float SINOB = fsin(OBECL);
+  float SXLONG = 0.f;
+  if (JULIAN >= 80.f) SXLONG = DPD * (JULIAN - 80.f) * DEGRAD;
+  if (JULIAN < 80.f) SXLONG = DPD * (JULIAN + 285.f) * DEGRAD;
+  const float ARG = SINOB * fsin(SXLONG);
+  const float DECLIN = fasin(ARG);
+  ForcingParams f;
+  // exactly at file A (hrldas_input_copy): bracket B is not needed, so a B upload still in flight is not waited for
+  // (A*1 + A*0 gives the same bits as A*1 + B*0 for finite data)
+  const bool needB = fraction != 1.0f;
+  for (int k = 0; k < 9; ++k) { f.A[k] = ctx->d_fb[0][k]; f.B[k] = needB ? ctx->d_fb[1][k] : ctx->d_fb[0][k]; }
+  f.lat = ctx->d_lat; f.lon = ctx->d_lon;
+  for (int k = 0; k < NFORC; ++k) f.out[k] = ctx->d_forc[k];
+  f.ncell = ctx->ncell;
+  f.fraction = fraction;
+  f.sin_declin = fsin(DECLIN);
+  f.cos_declin = fcos(DECLIN);
+  f.hour_frac = (float)ihour + (float)iminute / 60.0f + (float)isecond / 3600.0f;
+  f.dt = model_timestep;
+  f.zlvl = ctx->zlvl;
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fb[0], 0));
+  if (needB) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fb[1], 0));
+  if (parity) nmp_launch_forcing_parity(f, ctx->stream, &ctx->launches);
+  else nmp_launch_forcing_fast(f, ctx->stream, &ctx->launches);
+  CK(cudaGetLastError());
+  if (julian_out) *julian_out = JULIAN;
+  for (int k = 0; k < NFORC; ++k) ctx->base.forc[k] = ctx->d_forc[k];
+  return 0;
+}
+
+int noahmp_b200_noahmplsm_device_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp_status* status) {
+  if (!ctx || !a) return NOAHMP_ERR_ARG;
+  if (ctx->sync_mode != NOAHMP_SYNC_RESIDENT || !ctx->uploaded) {
+    set_error("noahmplsm_device_forcing needs RESIDENT mode and an uploaded state");
+    return NOAHMP_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = check_bounds(ctx, a))) return rc;
+  fill_scalars(ctx, a);
+  if ((rc = check_options(ctx))) return rc;
+  int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 8 : 1);
+  if (nch > ctx->nj) nch = ctx->nj;
+  if (ctx->fetch.empty()) nch = 1;
+  if ((rc = step_resident_pipelined(ctx, a, nch, /*upload=*/false))) return rc;
+  noahmp_status st;
+  decode_status(ctx, &st);
+  if (status) *status = st;
+  return st.code;
 }
 
 long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }

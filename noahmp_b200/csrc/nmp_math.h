@@ -223,6 +223,7 @@ NMP_HD float log10f_(float x) { return (float)(log_d((double)x) * 0.434294481903
 NMP_HD float powf_(float x, float y) { return (float)pow_d((double)x, (double)y); }
 NMP_HD float atanf_(float x)  { return (float)atan_d((double)x); }
 NMP_HD float cosf_(float x)   { double s, c; sincos_d((double)x, &s, &c); return (float)c; }
+NMP_HD float sinf_(float x)   { double s, c; sincos_d((double)x, &s, &c); return (float)s; }
 NMP_HD float tanf_(float x)   { double s, c; sincos_d((double)x, &s, &c); return (float)(s / c); }
 NMP_HD float acosf_(float x) {
   // acos(x) = 2 atan( sqrt((1-x)/(1+x)) ),  x in (-1,1]
@@ -230,6 +231,13 @@ NMP_HD float acosf_(float x) {
   if (xd >= 1.0) return 0.0f;
   if (xd <= -1.0) return 3.14159274f;
   return (float)(2.0 * atan_d(sqrt_d((1.0 - xd) / (1.0 + xd))));
+}
+NMP_HD float asinf_(float x) {
+  // asin(x) = atan( x / sqrt(1 - x^2) ),  |x| < 1
+  double xd = (double)x;
+  if (xd >= 1.0) return 1.57079637f;
+  if (xd <= -1.0) return -1.57079637f;
+  return (float)atan_d(xd / sqrt_d(1.0 - xd * xd));
 }
 NMP_HD float tanhf_(float x) {
   double xd = (double)x;

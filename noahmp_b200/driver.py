@@ -146,6 +146,33 @@ class NoahMP:
             raise KeyError(field)
         return _DevArray(p, (n.value,), "<i4" if field in _capi.INT_ARRAYS else "<f4")
 
+    # ---- forcing pipeline on the device (row f2) ---------------------------------------------------------
+    def forcing_static(self, lat2d, lon2d, zlvl=30.0):
+        self._keep = (np.ascontiguousarray(lat2d, np.float32), np.ascontiguousarray(lon2d, np.float32))
+        self._check_rc(self._L.noahmp_b200_forcing_static(self._ctx, self._keep[0].ctypes.data, self._keep[1].ctypes.data,
+                                                          zlvl))
+
+    def forcing_upload(self, slot, fields):
+        """fields: dict t q u v p lw sw pcp fpar of (nj, ni) float32 arrays = one forcing file; slot 0 = A, 1 = B.
+        The copy is asynchronous: keep the arrays alive and unchanged until the next forcing_apply returns."""
+        f = _capi.make_forcing_fields(fields)
+        self._check_rc(self._L.noahmp_b200_forcing_upload(self._ctx, slot, C.byref(f)))
+
+    def forcing_swap(self):
+        self._check_rc(self._L.noahmp_b200_forcing_swap(self._ctx))
+
+    def forcing_apply(self, fraction, iday, ihour, iminute, isecond, dt):
+        j = C.c_float()
+        self._check_rc(self._L.noahmp_b200_forcing_apply(self._ctx, fraction, iday, ihour, iminute, isecond, dt,
+                                                         C.byref(j)))
+        return j.value
+
+    def noahmplsm_device_forcing(self, arrays, scalars):
+        a = _capi.make_args(arrays, scalars)
+        st = _capi.NoahmpStatus()
+        self._check(self._L.noahmp_b200_noahmplsm_device_forcing(self._ctx, C.byref(a), C.byref(st)))
+        return st
+
     # ---- opt_run = 5 groundwater (WTABLE_mmf_noahmp) --------------------------------------------------
     def wtable(self, arrays, scalars):
         """CALL WTABLE_mmf_noahmp(...) on a tile that needs no halo (single tile = whole domain)."""

@@ -32,6 +32,8 @@ inline double DPOW(double x, double y) { return g_math_mode ? nmpm::pow_d(x, y) 
 inline float ATAN(float x)  { return g_math_mode ? nmpm::atanf_(x)  : std::atan(x); }
 inline float TAN(float x)   { return g_math_mode ? nmpm::tanf_(x)   : std::tan(x); }
 inline float COS(float x)   { return g_math_mode ? nmpm::cosf_(x)   : std::cos(x); }
+inline float SIN(float x)   { return g_math_mode ? nmpm::sinf_(x)   : std::sin(x); }
+inline float ASIN(float x)  { return g_math_mode ? nmpm::asinf_(x)  : std::asin(x); }
 inline float ACOS(float x)  { return g_math_mode ? nmpm::acosf_(x)  : std::acos(x); }
 inline float TANH(float x)  { return g_math_mode ? nmpm::tanhf_(x)  : std::tanh(x); }
 inline float SQRT(float x)  { return std::sqrt(x); }

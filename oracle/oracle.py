@@ -77,3 +77,19 @@ def wtable(arrays, scalars, tables_struct):
     rc = lib().nmo_wtable(C.byref(a), C.byref(tables_struct))
     if rc:
         raise RuntimeError(f"nmo_wtable failed: {rc}")
+
+
+def forcing(A, B, lat2d, lon2d, fraction, iday, ihour, iminute, isecond, dt, zlvl=30.0):
+    """Oracle of the driver-side forcing preparation. A, B: dicts of the 9 forcing-file fields. Returns
+    (list of the 12 forcing planes in NOAHMP_NFORCING order, JULIAN)."""
+    fa, fb = _capi.make_forcing_fields(A), _capi.make_forcing_fields(B)
+    lat = np.ascontiguousarray(lat2d, np.float32); lon = np.ascontiguousarray(lon2d, np.float32)
+    out = [np.zeros_like(lat) for _ in range(12)]
+    ptrs = (C.c_void_p * 12)(*[o.ctypes.data for o in out])
+    fn = lib().nmo_forcing
+    fn.restype = C.c_float
+    fn.argtypes = [C.POINTER(_capi.NoahmpForcingFields)] * 2 + [C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_int, C.c_int,
+                                                                C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    j = fn(C.byref(fa), C.byref(fb), lat.ctypes.data, lon.ctypes.data, lat.size, fraction, iday, ihour, iminute, isecond,
+           dt, zlvl, ptrs)
+    return out, j
