@@ -203,6 +203,12 @@ int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields);
 /* RESIDENT mode runs as a pipeline over `nchunks` row chunks (forcing upload | physics | result download overlap);
  * 0 = automatic. */
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
+/* Divergence control (north_star item 4): in RESIDENT mode the land columns are physically re-ordered every
+ * `interval` steps (default 20, 0 = never), inside their row chunk, into bins of equal snow-layer count and equal
+ * canopy-iteration count of the previous step, so the threads of a block take the same branches and leave the
+ * Newton loops together.  Results do not depend on the order; noahmp_b200_column_map returns the current one. */
+int noahmp_b200_set_rebin(noahmp_b200_ctx* ctx, int interval);
+int noahmp_b200_rebin_count(const noahmp_b200_ctx* ctx);
 /* Refresh ONE caller array (named like the noahmp_lsm_args member, e.g. "tsk") from HBM in RESIDENT mode. */
 int noahmp_b200_fetch(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, const char* field);
 

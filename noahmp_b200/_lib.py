@@ -36,6 +36,8 @@ SYMBOLS = {
     "noahmp_b200_noahmplsm": (C.c_int, [_ctx, _pa, _ps]),
     "noahmp_b200_sync_host": (C.c_int, [_ctx, _pa]),
     "noahmp_b200_set_fetch": (C.c_int, [_ctx, C.c_char_p]),
+    "noahmp_b200_set_rebin": (C.c_int, [_ctx, C.c_int]),
+    "noahmp_b200_rebin_count": (C.c_int, [_ctx]),
     "noahmp_b200_set_chunks": (C.c_int, [_ctx, C.c_int]),
     "noahmp_b200_fetch": (C.c_int, [_ctx, _pa, C.c_char_p]),
     "noahmp_b200_bind_forcing": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),

@@ -291,9 +291,7 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   s.PONDING = 0.f; s.PONDING1 = 0.f; s.PONDING2 = 0.f; s.QSNBOT = 0.f; s.FPICE = 0.f;
   NOAHMP_SFLX<O>(c, s, io);
   if (io.on && p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
-#if NMP_SORT
-  io.sti(nmpf::PLANE_PREV_ITERS, s.VEGE_ITERS);
-#endif
+  io.sti(nmpf::PLANE_PREV_ITERS, s.VEGE_ITERS);  // key of the column re-binning (nmp_lib.cu: rebin)
   if (live && c.err) report_error(p, io.cell, c.err, c.errv);
 }
 

@@ -5,6 +5,7 @@
 // rows (:399-419), the per-column gather/scatter (:449-512, :728-835) and the status convention that
 // stands in for wrf_error_fatal.  There is no CPU fallback: without a CUDA device create() fails.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -96,7 +97,15 @@ struct noahmp_b200_ctx {
   std::string variant;
   std::unordered_map<const void*, size_t> registered;
   // chunk pipeline of the RESIDENT-mode call
-  std::vector<int> h_cell;                 // host copy of the column map
+  std::vector<int> h_cell;                 // host copy of the column map (grid order, as classified)
+  // column re-binning (divergence control): land columns are physically re-ordered inside each row chunk by
+  // (canopy Newton passes of the previous step, snow-layer count)
+  int rebin_interval = 20, steps_since_rebin = 0, rebins = 0, bin_chunks = 0;
+  bool binned = false;
+  float* d_state2 = nullptr;
+  unsigned char* d_plane_kind = nullptr;
+  int *d_cell2 = nullptr, *d_keys = nullptr, *d_keys2 = nullptr, *d_perm = nullptr, *d_iota = nullptr, *d_chunk = nullptr;
+  std::vector<int> ch_land, ch_glac, ch_sea;  // compact range boundaries of the row chunks (size nchunks+1)
   std::vector<int> fetch;                  // fields refreshed on the host by every noahmplsm call
   int nchunks = 0;                         // 0 = automatic
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -380,6 +389,7 @@ static int classify(noahmp_b200_ctx* ctx) {
   ctx->nclass[CL_WATER] = (int)(nc - offset);
   if (ctx->np > ctx->np_alloc) {
     if (ctx->d_state) CK(cudaFree(ctx->d_state));
+    if (ctx->d_state2) { CK(cudaFree(ctx->d_state2)); ctx->d_state2 = nullptr; }
     CK(cudaMalloc(&ctx->d_state, sizeof(float) * (size_t)NPLANES_ALLOC * (size_t)ctx->np));
     CK(cudaMemsetAsync(ctx->d_state + (size_t)PLANE_PREV_ITERS * (size_t)ctx->np, 0, sizeof(float) * (size_t)ctx->np,
                        ctx->stream));
@@ -388,6 +398,9 @@ static int classify(noahmp_b200_ctx* ctx) {
   ctx->h_cell.resize((size_t)ctx->np);
   if (ctx->np) CK(cudaMemcpy(ctx->h_cell.data(), ctx->d_cell, sizeof(int) * ctx->np, cudaMemcpyDeviceToHost));
   ctx->classified = true;
+  ctx->binned = false;
+  ctx->bin_chunks = 0;
+  ctx->steps_since_rebin = 0;
   return 0;
 }
 
@@ -453,6 +466,9 @@ static void decode_status(noahmp_b200_ctx* ctx, noahmp_status* st) {
 
 // ---- C ABI ----------------------------------------------------------------------------------------------
 extern "C" {
+
+static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks);
+static int rebin(noahmp_b200_ctx* ctx);
 
 const char* noahmp_b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -525,6 +541,8 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   cudaFree(ctx->d_state); cudaFree(ctx->d_planes); cudaFree(ctx->d_cell); cudaFree(ctx->d_class);
   cudaFree(ctx->d_cub); cudaFree(ctx->d_nsel); cudaFree(ctx->d_errkey); cudaFree(ctx->d_errcount);
   cudaFree(ctx->d_vege_iters);
+  cudaFree(ctx->d_state2); cudaFree(ctx->d_cell2); cudaFree(ctx->d_keys); cudaFree(ctx->d_keys2);
+  cudaFree(ctx->d_perm); cudaFree(ctx->d_iota); cudaFree(ctx->d_chunk); cudaFree(ctx->d_plane_kind);
   for (auto& b : ctx->d_fb) for (auto p : b) cudaFree(p);
   cudaFree(ctx->d_lat); cudaFree(ctx->d_lon);
   for (auto e : ctx->ev_fb) if (e) cudaEventDestroy(e);
@@ -602,6 +620,18 @@ int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out) {
 int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt, void* stream) {
   if (!ctx || !ctx->uploaded) { set_error("step_device before upload"); return NOAHMP_ERR_ARG; }
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  if (ctx->sync_mode == NOAHMP_SYNC_RESIDENT && ctx->rebin_interval > 0 && ctx->nclass[CL_LAND] > 0) {
+    if (itimestep > 1 && (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
+      int nch = ctx->bin_chunks ? ctx->bin_chunks
+                                : (ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 8 : 1));
+      if (nch > ctx->nj) nch = ctx->nj;
+      int rc = chunk_ranges(ctx, nch);
+      if (rc) return rc;
+      CK(cudaDeviceSynchronize());  // earlier steps may be in flight on a caller stream
+      if ((rc = rebin(ctx))) return rc;
+    }
+    ctx->steps_since_rebin++;
+  }
   StepParams p = ctx->base;
   p.itimestep = itimestep;
   p.yearlen = year_length(yr);
@@ -649,6 +679,112 @@ int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
   if ((rc = scatter_fields(ctx))) return rc;
   if ((rc = download_state(ctx, a))) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- column re-binning -------------------------------------------------------------------------------------------
+// Row-chunk boundaries in the compact order.  Columns of a class are classified in grid order, so a row chunk is a
+// contiguous compact range per class; re-binning permutes land columns only INSIDE their chunk, which keeps these
+// ranges (and with them the upload | physics | download pipeline) valid.
+static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks) {
+  if (ctx->bin_chunks == nchunks && (int)ctx->ch_land.size() == nchunks + 1) return 0;
+  if (ctx->binned) { set_error("the number of row chunks cannot change after the columns were re-binned"); return NOAHMP_ERR_ARG; }
+  const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
+  const int* cl = ctx->h_cell.data();
+  auto lower = [&](int lo, int hi, int cell) { return (int)(std::lower_bound(cl + lo, cl + hi, cell) - cl); };
+  ctx->ch_land.assign(nchunks + 1, 0); ctx->ch_glac.assign(nchunks + 1, 0); ctx->ch_sea.assign(nchunks + 1, 0);
+  for (int c = 0; c <= nchunks; ++c) {
+    const int j = (int)((long long)ctx->nj * c / nchunks);
+    const int cell = j * ctx->ni;
+    ctx->ch_land[c] = c == nchunks ? nland : lower(0, nland, cell);
+    ctx->ch_glac[c] = c == nchunks ? nland + nglac : lower(nland, nland + nglac, cell);
+    ctx->ch_sea[c] = c == nchunks ? nland + nglac + nsea : lower(nland + nglac, nland + nglac + nsea, cell);
+  }
+  ctx->bin_chunks = nchunks;
+  return 0;
+}
+
+__global__ void bin_key_kernel(const float* __restrict__ state, long long np, int nland, const int* __restrict__ chunk_first,
+                               int nchunks, int* __restrict__ keys, int* __restrict__ iota) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nland) return;
+  int c = 0;
+  while (c + 1 < nchunks && n >= chunk_first[c + 1]) ++c;
+  const int isnow = __float_as_int(state[(long long)NMP_SLOT(isnowxy) * np + n]);
+  const int prev = __float_as_int(state[(long long)PLANE_PREV_ITERS * np + n]);
+  const int pb = prev == 0 ? 0 : (prev <= 6 ? 1 : (prev <= 8 ? 2 : (prev <= 12 ? 3 : 4)));
+  keys[n] = c * 32 + pb * 4 + min(max(-isnow, 0), 3);
+  iota[n] = n;
+}
+// new[plane][i] = old[plane][perm[i]] for land columns, plain copy for the other classes; blockIdx.y = plane
+// OUT planes (plane_kind 1) are rewritten for every land column by the step that follows, so only their non-land
+// tail is carried over.
+__global__ void permute_state_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ perm,
+                                     const unsigned char* __restrict__ plane_kind, long long np, int nland) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long long base = (long long)blockIdx.y * np;
+  if (i < nland) {
+    if (plane_kind[blockIdx.y] == 0) dst[base + i] = src[base + (long long)perm[i]];
+  } else {
+    dst[base + i] = src[base + i];
+  }
+}
+__global__ void permute_cell_kernel(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ perm,
+                                    long long np, int nland) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  dst[i] = src[i < nland ? (long long)perm[i] : i];
+}
+
+static int rebin(noahmp_b200_ctx* ctx) {
+  const int nland = ctx->nclass[CL_LAND];
+  const long long np = ctx->np;
+  const int nch = ctx->bin_chunks;
+  if (nland == 0 || nch == 0) return 0;
+  cudaStream_t s = ctx->stream;
+  if (!ctx->d_state2) {
+    CK(cudaMalloc(&ctx->d_state2, sizeof(float) * (size_t)NPLANES_ALLOC * (size_t)ctx->np_alloc));
+    CK(cudaMalloc(&ctx->d_cell2, sizeof(int) * ctx->ncell));
+    CK(cudaMalloc(&ctx->d_keys, sizeof(int) * ctx->ncell));
+    CK(cudaMalloc(&ctx->d_keys2, sizeof(int) * ctx->ncell));
+    CK(cudaMalloc(&ctx->d_perm, sizeof(int) * ctx->ncell));
+    CK(cudaMalloc(&ctx->d_iota, sizeof(int) * ctx->ncell));
+    CK(cudaMalloc(&ctx->d_chunk, sizeof(int) * 80));
+    std::vector<unsigned char> kind(NPLANES_ALLOC, 0);
+    for (int f = 0; f < NFIELDS; ++f)
+      for (int k = 0; k < kFields[f].layers; ++k) kind[kSlots.slot[f] + k] = (unsigned char)kFields[f].kind;
+    CK(cudaMalloc(&ctx->d_plane_kind, NPLANES_ALLOC));
+    CK(cudaMemcpy(ctx->d_plane_kind, kind.data(), NPLANES_ALLOC, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpyAsync(ctx->d_chunk, ctx->ch_land.data(), sizeof(int) * (nch + 1), cudaMemcpyHostToDevice, s));
+  const int T = 256;
+  bin_key_kernel<<<(nland + T - 1) / T, T, 0, s>>>(ctx->d_state, np, nland, ctx->d_chunk, nch, ctx->d_keys, ctx->d_iota);
+  ctx->launches++;
+  int bits = 5;
+  while ((1 << (bits - 5)) < nch) ++bits;
+  size_t need = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
+  if (need > ctx->cub_bytes) {
+    if (ctx->d_cub) CK(cudaFree(ctx->d_cub));
+    CK(cudaMalloc(&ctx->d_cub, need));
+    ctx->cub_bytes = need;
+  }
+  // stable LSD radix sort: columns of equal key keep their current relative order
+  CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
+  dim3 grid((unsigned)((np + T - 1) / T), NPLANES_ALLOC);
+  permute_state_kernel<<<grid, T, 0, s>>>(ctx->d_state, ctx->d_state2, ctx->d_perm, ctx->d_plane_kind, np, nland);
+  permute_cell_kernel<<<(unsigned)((np + T - 1) / T), T, 0, s>>>(ctx->d_cell, ctx->d_cell2, ctx->d_perm, np, nland);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  std::swap(ctx->d_state, ctx->d_state2);
+  std::swap(ctx->d_cell, ctx->d_cell2);
+  ctx->base.state = ctx->d_state;
+  ctx->base.cell = ctx->d_cell;
+  ctx->binned = true;
+  ctx->steps_since_rebin = 0;
+  ctx->rebins++;
   return 0;
 }
 
@@ -706,10 +842,15 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
     ctx->launches++;
   }
   const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
-  const int* cl = ctx->h_cell.data();
-  auto lower = [&](int lo, int hi, int cell) {  // first compact index in [lo,hi) whose cell >= `cell`
-    return (int)(std::lower_bound(cl + lo, cl + hi, cell) - cl);
-  };
+  int rc0 = chunk_ranges(ctx, nchunks);
+  if (rc0) return rc0;
+  if (ctx->rebin_interval > 0 && nland > 0 && a->itimestep > 1 &&
+      (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
+    if ((rc0 = rebin(ctx))) return rc0;
+    p.state = ctx->d_state;
+    p.cell = ctx->d_cell;
+  }
+  ctx->steps_since_rebin++;
   for (int c = 0; c < nchunks; ++c) {
     const int j0 = (int)((long long)nj * c / nchunks), j1 = (int)((long long)nj * (c + 1) / nchunks);
     if (j1 <= j0) continue;
@@ -721,16 +862,15 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
       CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
       CK(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
     }
-    const int c0 = j0 * ni, c1 = j1 * ni;
     StepRange r;
-    r.land_first = lower(0, nland, c0);
-    r.land_count = lower(0, nland, c1) - r.land_first;
-    r.glac_first = lower(nland, nland + nglac, c0);
-    r.glac_count = lower(nland, nland + nglac, c1) - r.glac_first;
+    r.land_first = ctx->ch_land[c];
+    r.land_count = ctx->ch_land[c + 1] - r.land_first;
+    r.glac_first = ctx->ch_glac[c];
+    r.glac_count = ctx->ch_glac[c + 1] - r.glac_first;
     const char* v = ctx->math_mode == NOAHMP_MATH_PARITY ? nmp_launch_step_parity(p, r, sk, &ctx->launches)
                                                          : nmp_launch_step_fast(p, r, sk, &ctx->launches);
     ctx->variant = v;
-    const int s0 = lower(nland + nglac, nland + nglac + nsea, c0), s1 = lower(nland + nglac, nland + nglac + nsea, c1);
+    const int s0 = ctx->ch_sea[c], s1 = ctx->ch_sea[c + 1];
     if (s1 > s0) {
       seaice_kernel<<<(s1 - s0 + 255) / 256, 256, 0, sk>>>(ctx->d_state, ctx->d_cell, ctx->d_stat[ST_XICE], ctx->np, s0,
                                                          s1 - s0, a->itimestep);
@@ -790,6 +930,14 @@ int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields) {
   ctx->fetch = list;
   return 0;
 }
+
+// Re-bin the land columns every `interval` RESIDENT-mode steps (0 = never).  Default 20.
+int noahmp_b200_set_rebin(noahmp_b200_ctx* ctx, int interval) {
+  if (!ctx || interval < 0) return NOAHMP_ERR_ARG;
+  ctx->rebin_interval = interval;
+  return 0;
+}
+int noahmp_b200_rebin_count(const noahmp_b200_ctx* ctx) { return ctx ? ctx->rebins : 0; }
 
 // Number of row chunks of the RESIDENT-mode pipeline (0 = automatic: 1 below 2^20 cells, else 8).
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks) {

@@ -124,6 +124,14 @@ class NoahMP:
         """Fields every RESIDENT-mode noahmplsm() call refreshes on the host (pipelined with the step)."""
         self._check(self._L.noahmp_b200_set_fetch(self._ctx, ",".join(fields).encode()))
 
+    def set_rebin(self, interval):
+        """Re-bin land columns every `interval` RESIDENT-mode steps (0 = never)."""
+        self._check(self._L.noahmp_b200_set_rebin(self._ctx, interval))
+
+    @property
+    def rebins(self):
+        return self._L.noahmp_b200_rebin_count(self._ctx)
+
     def set_chunks(self, n):
         self._check(self._L.noahmp_b200_set_chunks(self._ctx, n))
 

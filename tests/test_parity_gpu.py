@@ -189,6 +189,10 @@ def test_resident_mode_equals_full_sync(built, tables_usgs, chunks):
         for n in ("tsk", "tslb", "isnowxy"):
             assert np.array_equal(a[n], b[n]), (step, n)
     assert diff_report(a, b, ["hfx", "smois", "snow"])  # not fetched: still the initial host values
+    assert m2.rebins >= 1  # the land columns were physically re-binned on the way (divergence control)
+    cm = m2.column_map()
+    nl = m2.census()["land"]
+    assert sorted(cm[:nl].tolist()) == sorted(m1.column_map()[:nl].tolist()) and not np.array_equal(cm, m1.column_map())
     arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 8, st), b, 8)
     m2.sync_host(arr, sc)
     rep = diff_report(a, b)

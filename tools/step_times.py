@@ -1,0 +1,24 @@
+import sys, os, json, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+import noahmp_b200
+from noahmp_b200 import synthetic as S, tables
+interval=int(sys.argv[1]); ni,nj=2304,1920
+cfg=S.named_config("C3"); cfg.ni,cfg.nj=ni,nj
+td=tables.default_tables("USGS"); xp=S.backend()
+st=S.static_fields(xp,cfg); frc1=S.forcing(xp,cfg,1,st); state=S.cold_start(cfg,st,frc1,td)
+m=noahmp_b200.NoahMP(td,ni,nj,sync=noahmp_b200.SYNC_RESIDENT)
+m.set_rebin(interval)
+arr,sc=S.args_from(cfg,st,frc1,state,1); m.upload(arr,sc)
+dev=torch.device("cuda",0); xt=S.backend(dev); st_t=S.static_fields(xt,cfg)
+order=["coszin","t","qv","u","v","swdown","glw","p","p","rainbl","vegfra","dz8w"]
+ring=[]
+for h in range(4):
+    f=S.forcing(xt,cfg,1+h,st_t); pl={k:f[k].contiguous() for k in set(order)-{"vegfra","dz8w"}}
+    pl["vegfra"]=st_t["vegfra"].contiguous(); pl["dz8w"]=torch.full((nj,ni),60.0,device=dev); ring.append([pl[k] for k in order])
+torch.cuda.synchronize(); stream=torch.cuda.Stream(device=dev)
+ev=[torch.cuda.Event(enable_timing=True) for _ in range(31)]
+ev[0].record(stream)
+for k in range(30):
+    yr,jul,_=S.clock(cfg,1+k); m.bind_forcing([t.data_ptr() for t in ring[k%4]]); m.step_device(1+k,yr,float(jul),3600.0,stream.cuda_stream); ev[k+1].record(stream)
+torch.cuda.synchronize()
+print("interval",interval,"rebins",m.rebins," ".join("%.2f"%ev[k].elapsed_time(ev[k+1]) for k in range(30)))
