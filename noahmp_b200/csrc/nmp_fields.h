@@ -60,10 +60,12 @@ struct SlotTable {
 };
 constexpr SlotTable kSlots{};
 constexpr int NPLANES = kSlots.slot[NFIELDS];
-// internal planes after the argument-list fields: [NPLANES] = VEGE_FLUX pass count of the previous step (the
-// key of the in-block column sort of land_kernel)
+// internal planes after the argument-list fields: [NPLANES] = VEGE_FLUX pass count of the previous step (a key of
+// the column re-binning), then the NSTATIC static inputs in compact order (so that re-binned columns still read
+// them with unit stride)
 constexpr int PLANE_PREV_ITERS = NPLANES;
-constexpr int NPLANES_ALLOC = NPLANES + 1;
+constexpr int PLANE_STATIC0 = NPLANES + 1;
+constexpr int NPLANES_ALLOC = NPLANES + 1 + 7;
 template <int F>
 struct SlotOf {
   static constexpr int value = kSlots.slot[F];
@@ -76,6 +78,7 @@ enum ForcingId {
 };
 static_assert(NFORC == NOAHMP_NFORCING, "forcing plane count");
 enum StaticId { ST_IVGTYP = 0, ST_ISLTYP, ST_VEGMAX, ST_TMN, ST_XLATIN, ST_XLAND, ST_XICE, NSTATIC };
+static_assert(NPLANES_ALLOC == NPLANES + 1 + NSTATIC, "internal plane count");
 
 // column classes (noahmpdrv.F90:426-441)
 enum ColClass { CL_WATER = 0, CL_LAND = 1, CL_GLACIER = 2, CL_SEAICE = 3 };

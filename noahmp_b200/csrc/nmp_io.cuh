@@ -17,8 +17,9 @@ struct ColumnIO {
   bool on;      // stores enabled (false for the padding threads of the last block and for rejected columns)
   __device__ ColumnIO(const nmpf::StepParams& p_, long long n_, bool on_) : p(p_), n(n_), cell(p_.cell[n_]), on(on_) {}
   __device__ float forc(int f) const { return __ldg(p.forc[f] + cell); }
-  __device__ float stat(int f) const { return __ldg(p.stat[f] + cell); }
-  __device__ int stati(int f) const { return __float_as_int(__ldg(p.stat[f] + cell)); }
+  // static inputs: compact copies (planes PLANE_STATIC0 + f), unit stride also after re-binning
+  __device__ float stat(int f) const { return p.state[(long long)(nmpf::PLANE_STATIC0 + f) * p.np + n]; }
+  __device__ int stati(int f) const { return __float_as_int(stat(f)); }
   __device__ float ld(int slot) const { return p.state[(long long)slot * p.np + n]; }
   __device__ int ldi(int slot) const { return __float_as_int(p.state[(long long)slot * p.np + n]); }
   __device__ void st(int slot, float v) const { if (on) p.state[(long long)slot * p.np + n] = v; }

@@ -172,6 +172,14 @@ __global__ void scatter_kernel(const PlaneDesc* __restrict__ planes, const int* 
   d.grid[(long long)i + (long long)d.layer * ni + (long long)j * ni * d.layers] = state[(long long)d.plane * np + n];
 }
 
+// static inputs (grid order) -> their compact planes; blockIdx.y = static plane
+struct StatPtrs { const float* p[NSTATIC]; };
+__global__ void gather_static_kernel(StatPtrs st, const int* __restrict__ cell, float* state, long long np) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  state[(long long)(PLANE_STATIC0 + blockIdx.y) * np + n] = st.p[blockIdx.y][cell[n]];
+}
+
 // ITIMESTEP == 1 initialisation of open-water cells (noahmpdrv.F90:399-411); works on the grid-order staging
 // arrays because those cells have no compact column (the XICE == 1 branch lives in seaice_kernel).
 __global__ void first_step_water_kernel(const float* __restrict__ xland, const float* __restrict__ xice, float* smstav,
@@ -407,6 +415,13 @@ static int classify(noahmp_b200_ctx* ctx) {
 static int gather_fields(noahmp_b200_ctx* ctx) {
   if (ctx->np == 0) return 0;
   const int T = 256;
+  {
+    StatPtrs st;
+    for (int f = 0; f < NSTATIC; ++f) st.p[f] = ctx->d_stat[f];
+    dim3 g((unsigned)((ctx->np + T - 1) / T), NSTATIC);
+    gather_static_kernel<<<g, T, 0, ctx->stream>>>(st, ctx->d_cell, ctx->d_state, ctx->np);
+    ctx->launches++;
+  }
   dim3 grid((unsigned)((ctx->np + T - 1) / T), NPLANES);
   gather_kernel<<<grid, T, 0, ctx->stream>>>(ctx->d_planes, ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
   ctx->launches++;
