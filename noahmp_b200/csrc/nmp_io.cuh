@@ -24,6 +24,21 @@ struct ColumnIO {
   __device__ int ldi(int slot) const { return __float_as_int(p.state[(long long)slot * p.np + n]); }
   __device__ void st(int slot, float v) const { if (on) p.state[(long long)slot * p.np + n] = v; }
   __device__ void sti(int slot, int v) const { if (on) p.state[(long long)slot * p.np + n] = __int_as_float(v); }
+  // accumulator += v.  Production build: one fire-and-forget RED.ADD.F32 (no load latency in the dependency chain;
+  // a column has a single writer, so the sum is the same round-to-nearest add).  Parity build: load-add-store,
+  // because red.add.f32 flushes subnormals and the oracle does not.
+  __device__ void acc(int slot, float v) const {
+    if (!on) return;
+#if NMP_FASTMATH
+    atomicAdd(p.state + ((long long)slot * p.np + n), v);
+#else
+    p.state[(long long)slot * p.np + n] = p.state[(long long)slot * p.np + n] + v;
+#endif
+  }
+  // L2 prefetch of a plane element that is loaded late in the column program
+  __device__ void prefetch(int slot) const {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + ((long long)slot * p.np + n)));
+  }
 };
 
 }  // namespace nmp

@@ -257,6 +257,12 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   s.WA = io.ld(NMP_SLOT(waxy));  // for BEG_WB; reloaded with the rest of the water-table state before WATER
   s.LAI = io.ld(NMP_SLOT(xlaixy));
   s.SAI = io.ld(NMP_SLOT(xsaixy));
+  // state that NOAHMP_SFLX loads late (water table, carbon pools): start the HBM -> L2 transfer now
+  io.prefetch(NMP_SLOT(zwtxy)); io.prefetch(NMP_SLOT(wtxy)); io.prefetch(NMP_SLOT(smcwtdxy));
+  if (p.opt[0] == 2 || p.opt[0] == 5) {
+    io.prefetch(NMP_SLOT(lfmassxy)); io.prefetch(NMP_SLOT(rtmassxy)); io.prefetch(NMP_SLOT(stmassxy));
+    io.prefetch(NMP_SLOT(woodxy)); io.prefetch(NMP_SLOT(stblcpxy)); io.prefetch(NMP_SLOT(fastcpxy));
+  }
   // WSLAKE (IST = 1 always) and, unless dveg is 2 or 5, the carbon pools pass through NOAHMP_SFLX unchanged:
   // they stay where they are in HBM.  The remaining state is loaded inside NOAHMP_SFLX where first needed.
   s.ZWT = 0.f; s.WT = 0.f; s.SMCWTD = 0.f; s.WSLAKE = 0.f;

@@ -592,8 +592,8 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
   io.st(NMP_SLOT(qfx), s.ECAN + s.EDIR + s.ETRAN);
   io.st(NMP_SLOT(smstav), 0.0f);
   io.st(NMP_SLOT(smstot), 0.0f);
-  io.st(NMP_SLOT(sfcrunoff), io.ld(NMP_SLOT(sfcrunoff)) + s.RUNSRF * DTX);
-  io.st(NMP_SLOT(udrunoff), io.ld(NMP_SLOT(udrunoff)) + s.RUNSUB * DTX);
+  io.acc(NMP_SLOT(sfcrunoff), s.RUNSRF * DTX);
+  io.acc(NMP_SLOT(udrunoff), s.RUNSUB * DTX);
 #pragma unroll
   for (int K = 1; K <= NSOIL; ++K) {
     io.st(NMP_SLOT(smois) + K - 1, s.SMC(K));
@@ -602,8 +602,8 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
   io.st(NMP_SLOT(snow), s.SNEQV);
   io.st(NMP_SLOT(snowh), s.SNOWH);
   io.st(NMP_SLOT(canwat), s.CANLIQ + s.CANICE);
-  io.st(NMP_SLOT(acsnow), io.ld(NMP_SLOT(acsnow)) + s.PRCP * s.FPICE);
-  io.st(NMP_SLOT(acsnom), io.ld(NMP_SLOT(acsnom)) + s.QSNBOT * DTX + s.PONDING + s.PONDING1 + s.PONDING2);
+  io.acc(NMP_SLOT(acsnow), s.PRCP * s.FPICE);
+  io.acc(NMP_SLOT(acsnom), s.QSNBOT * DTX + s.PONDING + s.PONDING1 + s.PONDING2);
   io.st(NMP_SLOT(qsfc), s.QSFC);
   io.sti(NMP_SLOT(isnowxy), s.ISNOW);
   io.st(NMP_SLOT(tvxy), s.TV);
@@ -633,8 +633,8 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
   io.st(NMP_SLOT(ecanxy), s.ECAN);
   io.st(NMP_SLOT(edirxy), s.EDIR);
   io.st(NMP_SLOT(etranxy), s.ETRAN);
-  io.st(NMP_SLOT(rechxy), io.ld(NMP_SLOT(rechxy)) + s.RECH * 1.E3f);
-  io.st(NMP_SLOT(deeprechxy), io.ld(NMP_SLOT(deeprechxy)) + s.DEEPRECH);
+  io.acc(NMP_SLOT(rechxy), s.RECH * 1.E3f);
+  io.acc(NMP_SLOT(deeprechxy), s.DEEPRECH);
   io.st(NMP_SLOT(smcwtdxy), s.SMCWTD);
 }
 

@@ -22,3 +22,6 @@ for k in range(30):
     yr,jul,_=S.clock(cfg,1+k); m.bind_forcing([t.data_ptr() for t in ring[k%4]]); m.step_device(1+k,yr,float(jul),3600.0,stream.cuda_stream); ev[k+1].record(stream)
 torch.cuda.synchronize()
 print("interval",interval,"rebins",m.rebins," ".join("%.2f"%ev[k].elapsed_time(ev[k+1]) for k in range(30)))
+s=m.status(); print("status code",s.code,"count",s.count, "launches", m.launch_count() if hasattr(m,"launch_count") else None)
+for f in ("tsk","sfcrunoff","zwtxy","hfx"):
+    m.fetch(arr,sc,f); a=np.asarray(arr[f],dtype=np.float64); print(f,"mean %.6f min %.4f max %.4f nan %d"%(np.nanmean(a),np.nanmin(a),np.nanmax(a),int(np.isnan(a).sum())))
