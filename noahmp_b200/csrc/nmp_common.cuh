@@ -32,11 +32,6 @@
 #ifndef NMP_PHASE_SYNC
 #define NMP_PHASE_SYNC 0
 #endif
-// NMP_SORT: land_kernel assigns the columns of a block to its threads sorted by (snow-layer count, canopy Newton
-// passes of the previous step), so that the lanes of a warp take the same branches and leave loops together.
-#ifndef NMP_SORT
-#define NMP_SORT 0
-#endif
 // NMP_PHASE_SYNC: 0 = no barriers, 1 = barriers between all ~16 phases, 2 = only between the major phases
 #if NMP_PHASE_SYNC == 1
 #define NMP_PHASE() __syncthreads()
@@ -47,13 +42,6 @@
 #else
 #define NMP_PHASE() ((void)0)
 #define NMP_PHASE_MAJOR() ((void)0)
-#endif
-// barriers A (after the canopy loop) and B (after the ground loop) can be dropped separately (tuning sweeps)
-#ifndef NMP_SYNC_AFTER_VEGE
-#define NMP_SYNC_AFTER_VEGE 1
-#endif
-#ifndef NMP_SYNC_AFTER_BARE
-#define NMP_SYNC_AFTER_BARE 1
 #endif
 
 #define NMP_DEV __device__ __forceinline__

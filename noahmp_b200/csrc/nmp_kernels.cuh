@@ -211,32 +211,6 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   // the phase barriers inside NOAHMP_SFLX
   bool live = t < p.count;
   if (!live) t = p.count - 1;
-#if NMP_SORT
-  {
-    // In-block counting sort of the block's columns by divergence class.  The column -> thread assignment changes,
-    // the columns a block owns (and the coalescing of the block's accesses as a whole) do not, and neither do the
-    // results: a column's arithmetic does not depend on the thread that runs it.
-    constexpr int NBIN = 24;  // 4 snow-layer counts x 5 pass buckets, + padding bin
-    __shared__ int s_cnt[NBIN];
-    __shared__ int s_col[NMP_BLOCK];
-    if (threadIdx.x < NBIN) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const long long n0 = (long long)p.first + t;
-    const int isnow = __float_as_int(p.state[(long long)NMP_SLOT(isnowxy) * p.np + n0]);
-    const int prev = __float_as_int(p.state[(long long)nmpf::PLANE_PREV_ITERS * p.np + n0]);
-    const int pb = prev == 0 ? 0 : (prev <= 6 ? 1 : (prev <= 8 ? 2 : (prev <= 12 ? 3 : 4)));
-    const int bin = live ? pb * 4 + min(max(-isnow, 0), 3) : NBIN - 1;
-    const int pos = atomicAdd(&s_cnt[bin], 1);
-    __syncthreads();
-    int base = 0;
-    for (int b = 0; b < bin; ++b) base += s_cnt[b];
-    s_col[base + pos] = live ? t : -1;
-    __syncthreads();
-    const int mine = s_col[threadIdx.x];
-    live = mine >= 0;
-    t = live ? mine : p.count - 1;
-  }
-#endif
   ColumnIO io(p, (long long)p.first + t, live);
   Ctx c;
   init_ctx(c, p);
@@ -382,10 +356,6 @@ bool matches(const int* opt) {
 // Picks the specialised instantiation when the namelist options match one, else the generic kernel that
 // reads the options at run time.  Returns the name of the variant (for logs / tests).
 const char* launch_step(const StepParams& base, const nmpf::StepRange& r, cudaStream_t stream, long long* launches) {
-#ifdef NMP_ONLY_DYNVEG
-  launch_pair<OptDynVeg>(base, r, stream, launches);
-  return "dynveg";
-#endif
 #ifndef NMP_NO_SPECIALISE
   if (getenv("NOAHMP_B200_FORCE_RUNTIME")) {
     launch_pair<OptRuntime>(base, r, stream, launches);

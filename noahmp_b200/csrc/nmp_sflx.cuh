@@ -282,9 +282,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
     PSNSHA = vo.PSNSHA; s.Q2V = vo.Q2V; s.CHV2 = vo.CAH2; s.CHLEAF = vo.CHLEAF; s.CHUC = vo.CHUC;
   }
 
-#if NMP_SYNC_AFTER_VEGE
   NMP_PHASE_MAJOR();
-#endif
   s.TGB = s.TG;
   CMB = s.CM;
   s.CHB = s.CH;
@@ -294,9 +292,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
   s.CHB2 = bo.EHB2;
   (void)TAUXV; (void)TAUYV;
 
-#if NMP_SYNC_AFTER_BARE
   NMP_PHASE_MAJOR();
-#endif
   if (VEGTILE) {
     s.FIRA = s.FVEG * s.IRG + (1.0f - s.FVEG) * s.IRB + s.IRC;
     s.FSH = s.FVEG * s.SHG + (1.0f - s.FVEG) * s.SHB + s.SHC;
