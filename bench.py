@@ -40,6 +40,9 @@ N_SM, SCHED_PER_SM = 148, 4
 FORCING_ORDER = ["coszin", "t", "qv", "u", "v", "swdown", "glw", "p", "p", "rainbl", "vegfra", "dz8w"]
 
 
+PCIE_H2D_GBPS = 55.5  # PCIe 5 x16 of the B200 box, tools/pcie_probe.py
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -51,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, nargs=3, default=[1536, 1280, 16], help="ni nj steps of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunks", type=int, default=0, help="row chunks of the e2e pipeline (0 = library default)")
     ap.add_argument("--math", default="fast", choices=["fast", "parity"])
     return ap.parse_args()
 
@@ -215,6 +219,8 @@ def main():
     state = S.cold_start(cfg, st, frc1, td)
     math = noahmp_b200.MATH_PARITY if args.math == "parity" else noahmp_b200.MATH_FAST
     model = noahmp_b200.NoahMP(td, ni, nj, device=local, sync=noahmp_b200.SYNC_RESIDENT, math=math)
+    if args.chunks:
+        model.set_chunks(args.chunks)
     arr, sc = S.args_from(cfg, st, frc1, state, 1)
     sc.update(ims=xs, ime=xe, its=xs, ite=xe, jms=ys, jme=ye, jts=ys, jte=ye, ide=cfg.ni, jde=cfg.nj)
     model.upload(arr, sc)
@@ -409,8 +415,12 @@ def main():
         if e2e:
             line["e2e"] = {"value": ncol_all * args.steps / e2e_s_max, "unit": "column-steps/s",
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
-                           "call": "noahmp_b200_noahmplsm (RESIDENT state, set_fetch=tsk,hfx,lh,grdflx; 8 row chunks), pinned host buffers",
-                           "ms_per_step": 1e3 * e2e_s_max / args.steps}
+                           "call": "noahmp_b200_noahmplsm (RESIDENT state, set_fetch=tsk,hfx,lh,grdflx; 9 row chunks, half-height first and last), pinned host buffers",
+                           "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                           # the forcing upload is what bounds this call: bytes per rank / the box's pinned H2D rate
+                           "pcie_floor_ms": e2e[1] / PCIE_H2D_GBPS / 1e6,
+                           "pcie_note": f"{PCIE_H2D_GBPS} GB/s pinned H2D measured with tools/pcie_probe.py "
+                                        "(profiles/r01_pcie.json)"}
             line["e2e_forcing_pipeline"] = {
                 "value": ncol_all * args.steps / e2e_f2, "unit": "column-steps/s", "ms_per_step": 1e3 * e2e_f2 / args.steps,
                 "h2d_bytes_per_step": 9 * 4 * ni * nj // 3, "d2h_bytes_per_step": e2e[2],

@@ -10,6 +10,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -109,7 +110,9 @@ struct noahmp_b200_ctx {
   std::vector<int> fetch;                  // fields refreshed on the host by every noahmplsm call
   int nchunks = 0;                         // 0 = automatic
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  std::vector<cudaEvent_t> ev_in, ev_k;
+  std::vector<cudaEvent_t> ev_in, ev_k, ev_out, ev_plane;
+  cudaEvent_t ev_t0 = nullptr;
+  bool trace = false;  // NOAHMP_B200_TRACE: print the per-chunk timeline of every RESIDENT-mode call
   // opt_run = 5 groundwater: grid-order planes (see WtPlane) and the haloed KCELL / HEAD planes
   float* d_wt[12] = {};
   float *d_kcell = nullptr, *d_head = nullptr;
@@ -567,6 +570,9 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   if (ctx->h_errcount) cudaFreeHost(ctx->h_errcount);
   for (auto e : ctx->ev_in) cudaEventDestroy(e);
   for (auto e : ctx->ev_k) cudaEventDestroy(e);
+  for (auto e : ctx->ev_out) cudaEventDestroy(e);
+  for (auto e : ctx->ev_plane) if (e) cudaEventDestroy(e);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -638,7 +644,7 @@ int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float j
   if (ctx->sync_mode == NOAHMP_SYNC_RESIDENT && ctx->rebin_interval > 0 && ctx->nclass[CL_LAND] > 0) {
     if (itimestep > 1 && (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
       int nch = ctx->bin_chunks ? ctx->bin_chunks
-                                : (ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 8 : 1));
+                                : (ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 9 : 1));
       if (nch > ctx->nj) nch = ctx->nj;
       int rc = chunk_ranges(ctx, nch);
       if (rc) return rc;
@@ -701,6 +707,14 @@ int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
 // Row-chunk boundaries in the compact order.  Columns of a class are classified in grid order, so a row chunk is a
 // contiguous compact range per class; re-binning permutes land columns only INSIDE their chunk, which keeps these
 // ranges (and with them the upload | physics | download pipeline) valid.
+// First row of chunk c.  The first and the last chunk are half as tall as the others: the physics starts after a
+// short first upload and the step ends with a short last kernel + download (the pipeline's fill and drain).
+static int chunk_row(const noahmp_b200_ctx* ctx, int c, int nchunks) {
+  if (nchunks < 4) return (int)((long long)ctx->nj * c / nchunks);
+  const int units = 2 * nchunks - 2;
+  const int u = c <= 0 ? 0 : (c >= nchunks ? units : 2 * c - 1);
+  return (int)((long long)ctx->nj * u / units);
+}
 static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks) {
   if (ctx->bin_chunks == nchunks && (int)ctx->ch_land.size() == nchunks + 1) return 0;
   if (ctx->binned) { set_error("the number of row chunks cannot change after the columns were re-binned"); return NOAHMP_ERR_ARG; }
@@ -709,7 +723,7 @@ static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks) {
   auto lower = [&](int lo, int hi, int cell) { return (int)(std::lower_bound(cl + lo, cl + hi, cell) - cl); };
   ctx->ch_land.assign(nchunks + 1, 0); ctx->ch_glac.assign(nchunks + 1, 0); ctx->ch_sea.assign(nchunks + 1, 0);
   for (int c = 0; c <= nchunks; ++c) {
-    const int j = (int)((long long)ctx->nj * c / nchunks);
+    const int j = chunk_row(ctx, c, nchunks);
     const int cell = j * ctx->ni;
     ctx->ch_land[c] = c == nchunks ? nland : lower(0, nland, cell);
     ctx->ch_glac[c] = c == nchunks ? nland + nglac : lower(nland, nland + nglac, cell);
@@ -821,17 +835,27 @@ static int h2d_rows(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, 
 // Columns of a class are stored in grid order, so a row chunk is one contiguous compact range per class.
 static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, int nchunks, bool upload = true) {
   const int nk = a->kme - a->kms + 1, kms = a->kms, ni = ctx->ni, nj = ctx->nj;
+  const auto t_begin = std::chrono::steady_clock::now();
   if (!ctx->s_in) {
-    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    const unsigned sf = getenv("NOAHMP_B200_STREAMFLAGS") ? cudaStreamDefault : cudaStreamNonBlocking;
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, sf));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, sf));
   }
+  if (!ctx->ev_t0) {
+    ctx->trace = getenv("NOAHMP_B200_TRACE") != nullptr;
+    CK(cudaEventCreate(&ctx->ev_t0));
+  }
+  const unsigned evflags = ctx->trace ? cudaEventDefault : cudaEventDisableTiming;
   while ((int)ctx->ev_in.size() < nchunks) {
-    cudaEvent_t e1, e2;
-    CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    cudaEvent_t e1, e2, e3;
+    CK(cudaEventCreateWithFlags(&e1, evflags));
+    CK(cudaEventCreateWithFlags(&e2, evflags));
+    CK(cudaEventCreateWithFlags(&e3, evflags));
     ctx->ev_in.push_back(e1);
     ctx->ev_k.push_back(e2);
+    ctx->ev_out.push_back(e3);
   }
+  if (ctx->trace) CK(cudaEventRecord(ctx->ev_t0, ctx->s_in));
   struct Plane { int id; const float* src; int nk, lev; };
   const Plane planes[NFORC] = {
       {FC_COSZIN, a->coszin, 1, 1}, {FC_T, a->t3d, nk, 1},       {FC_QV, a->qv3d, nk, 1},      {FC_U, a->u_phy, nk, 1},
@@ -841,6 +865,9 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
     for (const Plane& pl : planes) pin(ctx, pl.src, sizeof(float) * (size_t)ni * nj * pl.nk);
   for (int f : ctx->fetch) pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
 
+  // host forcing supersedes device pointers bound earlier with bind_forcing()
+  if (upload)
+    for (int f = 0; f < NFORC; ++f) ctx->base.forc[f] = ctx->d_forc[f];
   StepParams p = ctx->base;
   p.itimestep = a->itimestep;
   p.yearlen = year_length(a->yr);
@@ -856,7 +883,7 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
         ctx->d_grid[F_tslb], ctx->ni, ctx->ncell);
     ctx->launches++;
   }
-  const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
+  const int nland = ctx->nclass[CL_LAND];
   int rc0 = chunk_ranges(ctx, nchunks);
   if (rc0) return rc0;
   if (ctx->rebin_interval > 0 && nland > 0 && a->itimestep > 1 &&
@@ -867,12 +894,17 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
   }
   ctx->steps_since_rebin++;
   for (int c = 0; c < nchunks; ++c) {
-    const int j0 = (int)((long long)nj * c / nchunks), j1 = (int)((long long)nj * (c + 1) / nchunks);
+    const int j0 = chunk_row(ctx, c, nchunks), j1 = chunk_row(ctx, c + 1, nchunks);
     if (j1 <= j0) continue;
     if (upload) {
       for (const Plane& pl : planes) {
         int rc = h2d_rows(ctx, ctx->d_forc[pl.id], pl.src, pl.nk, kms, pl.lev, j0, j1, ctx->s_in);
         if (rc) return rc;
+        if (ctx->trace && c == 0) {
+          if ((int)ctx->ev_plane.size() <= pl.id) ctx->ev_plane.resize(NFORC, nullptr);
+          if (!ctx->ev_plane[pl.id]) CK(cudaEventCreate(&ctx->ev_plane[pl.id]));
+          CK(cudaEventRecord(ctx->ev_plane[pl.id], ctx->s_in));
+        }
       }
       CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
       CK(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
@@ -911,13 +943,42 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
         CK(cudaMemcpyAsync(host_ptr(a, f) + off, ctx->d_grid[f] + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost,
                            ctx->s_out));
       }
+      if (ctx->trace) CK(cudaEventRecord(ctx->ev_out[c], ctx->s_out));
+    } else if (ctx->trace) {
+      CK(cudaEventRecord(ctx->ev_k[c], sk));
     }
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_errkey, ctx->d_errkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sk));
   CK(cudaMemcpyAsync(ctx->h_errcount, ctx->d_errcount, sizeof(int), cudaMemcpyDeviceToHost, sk));
+  const auto t_enq = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(sk));
   if (!ctx->fetch.empty()) CK(cudaStreamSynchronize(ctx->s_out));
+  if (ctx->trace) {
+    fprintf(stderr, "[noahmp_b200 trace] host: enqueue %.2f ms, total %.2f ms\n",
+            std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    // completion times (ms after the call's first enqueue): forcing rows up | physics (+ scatter) | results down
+    fprintf(stderr, "[noahmp_b200 trace] step %d:", a->itimestep);
+    for (int c = 0; c < nchunks; ++c) {
+      float t[3] = {-1.f, -1.f, -1.f};
+      if (upload) cudaEventElapsedTime(&t[0], ctx->ev_t0, ctx->ev_in[c]);
+      cudaEventElapsedTime(&t[1], ctx->ev_t0, ctx->ev_k[c]);
+      if (!ctx->fetch.empty()) cudaEventElapsedTime(&t[2], ctx->ev_t0, ctx->ev_out[c]);
+      fprintf(stderr, " [%d] %.2f|%.2f|%.2f", c, t[0], t[1], t[2]);
+    }
+    fprintf(stderr, "\n");
+    if (upload && !ctx->ev_plane.empty()) {
+      fprintf(stderr, "[noahmp_b200 trace] chunk 0 forcing planes up at:");
+      for (int f = 0; f < NFORC; ++f) {
+        float t = -1.f;
+        if (ctx->ev_plane[f]) cudaEventElapsedTime(&t, ctx->ev_t0, ctx->ev_plane[f]);
+        fprintf(stderr, " %.2f", t);
+      }
+      fprintf(stderr, "\n");
+    }
+    cudaGetLastError();
+  }
   return 0;
 }
 
@@ -972,7 +1033,7 @@ int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp
     if ((rc = check_bounds(ctx, a))) return rc;
     fill_scalars(ctx, a);
     if ((rc = check_options(ctx))) return rc;
-    int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 8 : 1);
+    int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 9 : 1);
     if (nch > ctx->nj) nch = ctx->nj;
     if ((rc = step_resident_pipelined(ctx, a, nch))) return rc;
     noahmp_status st;
@@ -1338,7 +1399,7 @@ int noahmp_b200_noahmplsm_device_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_
   if ((rc = check_bounds(ctx, a))) return rc;
   fill_scalars(ctx, a);
   if ((rc = check_options(ctx))) return rc;
-  int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 8 : 1);
+  int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 9 : 1);
   if (nch > ctx->nj) nch = ctx->nj;
   if (ctx->fetch.empty()) nch = 1;
   if ((rc = step_resident_pipelined(ctx, a, nch, /*upload=*/false))) return rc;

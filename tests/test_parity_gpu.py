@@ -184,6 +184,10 @@ def test_resident_mode_equals_full_sync(built, tables_usgs, chunks):
         frc = S.forcing(xp, cfg, step, st)
         arr_a, sc = S.args_from(cfg, st, frc, a, step)
         arr_b, _ = S.args_from(cfg, st, frc, b, step)
+        if step == 4:  # device pointers bound earlier must not survive a call that brings host forcing
+            import torch
+            junk = torch.full((cfg.nj, cfg.ni), 1.0e3, device="cuda")
+            m2.bind_forcing([junk.data_ptr()] * 12)
         s1, s2 = m1.noahmplsm(arr_a, sc), m2.noahmplsm(arr_b, sc)
         assert (s1.code, s1.count) == (s2.code, s2.count) == (0, 0)
         for n in ("tsk", "tslb", "isnowxy"):

@@ -99,3 +99,14 @@ for stall in ("stall_long_sb", "stall_barrier", "stall_wait"):
         byf[fn(ins[i])] += int(r[ix[stall]])
     tot_s = sum(byf.values()) or 1
     print(stall, "by function:", ", ".join(f"{k} {v / tot_s:.2f}" for k, v in byf.most_common(10)))
+# hottest source lines (innermost inlined location) by stall samples
+byl = {s: collections.Counter() for s in ("stall_long_sb", "stall_wait", "# Samples")}
+for i, r in enumerate(data):
+    for s in byl:
+        byl[s][ins[i]] += int(r[ix[s]])
+for s, c in byl.items():
+    t = sum(c.values()) or 1
+    print(f"top lines by {s}:")
+    for loc, v in c.most_common(14):
+        if loc:
+            print("   %-20s:%-5d %-14s %.3f" % (loc[0], loc[1], fn(loc), v / t))
