@@ -141,6 +141,7 @@ enum {
   NOAHMP_ERR_ZLVL = 6,     /* "STOP in Noah-MP" ZLVL <= ZPD (noahmplsm.F90:4124)          */
   NOAHMP_ERR_REDPRM = 7,   /* REDPRM range checks (noahmplsm.F90:9266-9277, :9340)        */
   NOAHMP_ERR_OPTION = 8,   /* unsupported option value (opt_sfc 3/4: non-functional offline) */
+  NOAHMP_ERR_ISLTYP = 9,   /* NOAHMP_INIT: ISLTYP < 1 (noahmpdrv.F90:1008-1021)            */
   NOAHMP_ERR_CUDA = 100,   /* CUDA runtime failure; see noahmp_b200_last_error()          */
   NOAHMP_ERR_ARG = 101
 };
@@ -306,6 +307,53 @@ int noahmp_b200_wtable_end(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args)
  * (NCCL send/recv through its own communicator) between _begin and _end. */
 int noahmp_b200_wtable_halo(noahmp_b200_ctx* ctx, float** kcell, float** head);
 int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
+
+/* ---- cold start: replaces `CALL NOAHMP_INIT(...)` -------------------------------
+ * phys/module_sf_noahmpdrv.F90:847-1179 with SNOW_INIT :1182-1283, GROUNDWATER_INIT :1286-1470 and EQSMOISTURE
+ * :1473-1522; call site driver/module_hrldas_noahmp_driver.F90:281-297.  One member per dummy argument, same names,
+ * same order; LOGICALs are int32 (0 = .FALSE.).  MMINLU is not needed (the context already holds the tables that
+ * read_mp_veg_parameters / SOIL_VEG_GEN_PARM would read); allowed_to_read is accepted and ignored for the same
+ * reason.  2-D arrays (ims:ime,jms:jme); TSLB/SMOIS/SH2O/SMOISEQ (ims:ime,1:nsoil,jms:jme); TSNOXY/SNICEXY/SNLIQXY
+ * (ims:ime,-2:0,jms:jme); ZSNSOXY (ims:ime,-2:nsoil,jms:jme).  The groundwater members may be NULL unless
+ * iopt_run == 5.  With restart != 0 nothing is touched, as in the reference. */
+typedef struct noahmp_init_args {
+  float *snow, *snowh, *canwat;
+  const int32_t *isltyp, *ivgtyp;
+  int32_t isurban;
+  float *tslb, *smois, *sh2o;
+  const float* dzs;
+  int32_t fndsoilw, fndsnowh, isice, iswater;
+  const float* tsk;
+  int32_t* isnowxy;
+  float *tvxy, *tgxy, *canicexy;
+  float* tmn;
+  const float* xice;
+  float *canliqxy, *eahxy, *tahxy, *cmxy, *chxy;
+  float *fwetxy, *sneqvoxy, *alboldxy, *qsnowxy, *wslakexy, *zwtxy, *waxy;
+  float *wtxy, *tsnoxy, *zsnsoxy, *snicexy, *snliqxy, *lfmassxy, *rtmassxy;
+  float *stmassxy, *woodxy, *stblcpxy, *fastcpxy, *xsaixy;
+  float *t2mvxy, *t2mbxy, *chstarxy;
+  int32_t nsoil, restart, allowed_to_read, iopt_run;
+  int32_t ids, ide, jds, jde, kds, kde;
+  int32_t ims, ime, jms, jme, kms, kme;
+  int32_t its, ite, jts, jte, kts, kte;
+  /* optional groundwater block */
+  float *smoiseq, *smcwtdxy, *rechxy, *deeprechxy, *areaxy;
+  float dx, dy;
+  const float *msftx, *msfty;
+  float wtddt;      /* minutes */
+  int32_t* stepwtd; /* OUT: max(nint(wtddt*60/dt),1) */
+  float dt;
+  float *qrfsxy, *qspringsxy, *qslatxy;
+  const float *fdepthxy, *ht, *riverbedxy, *eqzwt, *rivercondxy, *pexpxy;
+} noahmp_init_args;
+
+/* Uploads the arrays, runs the initialisation kernels, downloads the results into the caller's arrays.  Returns
+ * NOAHMP_ERR_ISLTYP when a cell of the tile has ISLTYP < 1 ("lsminit: out of range value of ISLTYP", :1018-1020),
+ * NOAHMP_ERR_ARG when iopt_run == 5 and a groundwater member is missing ("Not enough fields to use groundwater
+ * option in Noah-MP", :1171). */
+int noahmp_b200_init(noahmp_b200_ctx* ctx, const noahmp_init_args* args);
+unsigned long long noahmp_b200_sizeof_init_args(void);
 
 /* ---- domain decomposition: replaces mpp_land_partition arithmetic ----------------------------
  * mpp/module_mpp_land.F90:124-141 (process grid), :245-288 (tile extents). All 1-based inclusive. */

@@ -179,6 +179,101 @@ MODULE module_sf_noahmpdrv_b200
     REAL(C_FLOAT)  :: value
   END TYPE noahmp_status
 
+  !> member for member include/noahmp_b200.h :: noahmp_init_args (the NOAHMP_INIT dummy list)
+  TYPE, BIND(C) :: noahmp_init_args
+    TYPE(C_PTR) :: snow
+    TYPE(C_PTR) :: snowh
+    TYPE(C_PTR) :: canwat
+    TYPE(C_PTR) :: isltyp
+    TYPE(C_PTR) :: ivgtyp
+    INTEGER(C_INT) :: isurban
+    TYPE(C_PTR) :: tslb
+    TYPE(C_PTR) :: smois
+    TYPE(C_PTR) :: sh2o
+    TYPE(C_PTR) :: dzs
+    INTEGER(C_INT) :: fndsoilw
+    INTEGER(C_INT) :: fndsnowh
+    INTEGER(C_INT) :: isice
+    INTEGER(C_INT) :: iswater
+    TYPE(C_PTR) :: tsk
+    TYPE(C_PTR) :: isnowxy
+    TYPE(C_PTR) :: tvxy
+    TYPE(C_PTR) :: tgxy
+    TYPE(C_PTR) :: canicexy
+    TYPE(C_PTR) :: tmn
+    TYPE(C_PTR) :: xice
+    TYPE(C_PTR) :: canliqxy
+    TYPE(C_PTR) :: eahxy
+    TYPE(C_PTR) :: tahxy
+    TYPE(C_PTR) :: cmxy
+    TYPE(C_PTR) :: chxy
+    TYPE(C_PTR) :: fwetxy
+    TYPE(C_PTR) :: sneqvoxy
+    TYPE(C_PTR) :: alboldxy
+    TYPE(C_PTR) :: qsnowxy
+    TYPE(C_PTR) :: wslakexy
+    TYPE(C_PTR) :: zwtxy
+    TYPE(C_PTR) :: waxy
+    TYPE(C_PTR) :: wtxy
+    TYPE(C_PTR) :: tsnoxy
+    TYPE(C_PTR) :: zsnsoxy
+    TYPE(C_PTR) :: snicexy
+    TYPE(C_PTR) :: snliqxy
+    TYPE(C_PTR) :: lfmassxy
+    TYPE(C_PTR) :: rtmassxy
+    TYPE(C_PTR) :: stmassxy
+    TYPE(C_PTR) :: woodxy
+    TYPE(C_PTR) :: stblcpxy
+    TYPE(C_PTR) :: fastcpxy
+    TYPE(C_PTR) :: xsaixy
+    TYPE(C_PTR) :: t2mvxy
+    TYPE(C_PTR) :: t2mbxy
+    TYPE(C_PTR) :: chstarxy
+    INTEGER(C_INT) :: nsoil
+    INTEGER(C_INT) :: restart
+    INTEGER(C_INT) :: allowed_to_read
+    INTEGER(C_INT) :: iopt_run
+    INTEGER(C_INT) :: ids
+    INTEGER(C_INT) :: ide
+    INTEGER(C_INT) :: jds
+    INTEGER(C_INT) :: jde
+    INTEGER(C_INT) :: kds
+    INTEGER(C_INT) :: kde
+    INTEGER(C_INT) :: ims
+    INTEGER(C_INT) :: ime
+    INTEGER(C_INT) :: jms
+    INTEGER(C_INT) :: jme
+    INTEGER(C_INT) :: kms
+    INTEGER(C_INT) :: kme
+    INTEGER(C_INT) :: its
+    INTEGER(C_INT) :: ite
+    INTEGER(C_INT) :: jts
+    INTEGER(C_INT) :: jte
+    INTEGER(C_INT) :: kts
+    INTEGER(C_INT) :: kte
+    TYPE(C_PTR) :: smoiseq
+    TYPE(C_PTR) :: smcwtdxy
+    TYPE(C_PTR) :: rechxy
+    TYPE(C_PTR) :: deeprechxy
+    TYPE(C_PTR) :: areaxy
+    REAL(C_FLOAT) :: dx
+    REAL(C_FLOAT) :: dy
+    TYPE(C_PTR) :: msftx
+    TYPE(C_PTR) :: msfty
+    REAL(C_FLOAT) :: wtddt
+    TYPE(C_PTR) :: stepwtd
+    REAL(C_FLOAT) :: dt
+    TYPE(C_PTR) :: qrfsxy
+    TYPE(C_PTR) :: qspringsxy
+    TYPE(C_PTR) :: qslatxy
+    TYPE(C_PTR) :: fdepthxy
+    TYPE(C_PTR) :: ht
+    TYPE(C_PTR) :: riverbedxy
+    TYPE(C_PTR) :: eqzwt
+    TYPE(C_PTR) :: rivercondxy
+    TYPE(C_PTR) :: pexpxy
+  END TYPE noahmp_init_args
+
   INTEGER(C_INT), PARAMETER :: NOAHMP_SYNC_FULL = 0, NOAHMP_SYNC_RESIDENT = 1
   INTEGER, PARAMETER :: NOAHMP_TABLES_BYTES = 12712   ! sizeof(noahmp_tables); checked at start-up
 
@@ -212,6 +307,9 @@ MODULE module_sf_noahmpdrv_b200
     END FUNCTION
     FUNCTION noahmp_b200_sync_host(c, args) BIND(C, NAME="noahmp_b200_sync_host") RESULT(rc)
       IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_lsm_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_init(c, args) BIND(C, NAME="noahmp_b200_init") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_init_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
     END FUNCTION
   END INTERFACE
 
@@ -600,5 +698,149 @@ CONTAINS
       CALL wrf_error_fatal(TRIM(msg))
     END IF
   END SUBROUTINE noahmplsm
+
+  !> Drop-in for NOAHMP_INIT (phys/module_sf_noahmpdrv.F90:847-1179): same name, dummy list and order.  The tables are
+  !> those noahmp_b200_start() read; call it after noahmp_b200_start().
+  SUBROUTINE NOAHMP_INIT ( MMINLU, SNOW , SNOWH , CANWAT , ISLTYP ,   IVGTYP, ISURBAN, &
+       TSLB , SMOIS , SH2O , DZS , FNDSOILW , FNDSNOWH ,   ISICE,iswater  ,             &
+       TSK, isnowxy , tvxy     ,tgxy     ,canicexy ,         TMN,     XICE,   &
+       canliqxy ,eahxy    ,tahxy    ,cmxy     ,chxy     ,                     &
+       fwetxy   ,sneqvoxy ,alboldxy ,qsnowxy  ,wslakexy ,zwtxy    ,waxy     , &
+       wtxy     ,tsnoxy   ,zsnsoxy  ,snicexy  ,snliqxy  ,lfmassxy ,rtmassxy , &
+       stmassxy ,woodxy   ,stblcpxy ,fastcpxy , xsaixy   , &
+       t2mvxy   ,t2mbxy   ,chstarxy,            &
+       NSOIL, restart,                 &
+       allowed_to_read , iopt_run,                         &
+       ids,ide, jds,jde, kds,kde,                &
+       ims,ime, jms,jme, kms,kme,                &
+       its,ite, jts,jte, kts,kte,                &
+       smoiseq  ,smcwtdxy ,rechxy   ,deeprechxy, areaxy, dx, dy, msftx, msfty,&
+       wtddt    ,stepwtd  ,dt       ,qrfsxy     ,qspringsxy  , qslatxy    ,  &
+       fdepthxy ,ht     ,riverbedxy ,eqzwt     ,rivercondxy ,pexpxy            )
+    CHARACTER(LEN=*), INTENT(IN) :: MMINLU
+    INTEGER, INTENT(IN) :: ids,ide, jds,jde, kds,kde, ims,ime, jms,jme, kms,kme, its,ite, jts,jte, kts,kte
+    INTEGER, INTENT(IN) :: NSOIL, ISICE, ISWATER, ISURBAN, iopt_run
+    LOGICAL, INTENT(IN) :: restart, allowed_to_read, FNDSOILW, FNDSNOWH
+    REAL, DIMENSION(NSOIL), INTENT(IN), TARGET :: DZS
+    REAL, INTENT(IN), OPTIONAL :: DX, DY, DT, WTDDT
+    INTEGER, INTENT(OUT), OPTIONAL, TARGET :: STEPWTD
+    INTEGER, DIMENSION(ims:ime,jms:jme), INTENT(IN), TARGET :: ISLTYP, IVGTYP
+    INTEGER, DIMENSION(ims:ime,jms:jme), INTENT(INOUT), TARGET :: isnowxy
+    REAL, DIMENSION(ims:ime,jms:jme), INTENT(IN), TARGET :: TSK, XICE
+    REAL, DIMENSION(ims:ime,jms:jme), INTENT(INOUT), TARGET :: TMN
+    REAL, DIMENSION(ims:ime,jms:jme), INTENT(INOUT), TARGET :: &
+         snow, snowh, canwat, tvxy, tgxy, canicexy, canliqxy, eahxy, tahxy, cmxy, chxy, fwetxy, sneqvoxy, alboldxy, &
+         qsnowxy, wslakexy, zwtxy, waxy, wtxy, lfmassxy, rtmassxy, stmassxy, woodxy, stblcpxy, fastcpxy, xsaixy, t2mvxy, t2mbxy, chstarxy
+    REAL, DIMENSION(ims:ime,NSOIL,jms:jme), INTENT(INOUT), TARGET :: tslb
+    REAL, DIMENSION(ims:ime,NSOIL,jms:jme), INTENT(INOUT), TARGET :: smois
+    REAL, DIMENSION(ims:ime,NSOIL,jms:jme), INTENT(INOUT), TARGET :: sh2o
+    REAL, DIMENSION(ims:ime,-2:0,jms:jme), INTENT(INOUT), TARGET :: tsnoxy
+    REAL, DIMENSION(ims:ime,-2:0,jms:jme), INTENT(INOUT), TARGET :: snicexy
+    REAL, DIMENSION(ims:ime,-2:0,jms:jme), INTENT(INOUT), TARGET :: snliqxy
+    REAL, DIMENSION(ims:ime,-2:NSOIL,jms:jme), INTENT(INOUT), TARGET :: zsnsoxy
+    REAL, DIMENSION(ims:ime,1:NSOIL,jms:jme), INTENT(INOUT), OPTIONAL, TARGET :: smoiseq
+    REAL, DIMENSION(ims:ime,jms:jme), INTENT(INOUT), OPTIONAL, TARGET :: smcwtdxy, rechxy, deeprechxy, areaxy, qrfsxy, qspringsxy, qslatxy
+    REAL, DIMENSION(ims:ime,jms:jme), INTENT(IN), OPTIONAL, TARGET :: msftx, msfty, fdepthxy, ht, riverbedxy, eqzwt, rivercondxy, pexpxy
+    TYPE(noahmp_init_args) :: a
+    INTEGER(C_INT) :: rc
+
+    a%snow = C_LOC(snow)
+    a%snowh = C_LOC(snowh)
+    a%canwat = C_LOC(canwat)
+    a%isltyp = C_LOC(isltyp)
+    a%ivgtyp = C_LOC(ivgtyp)
+    a%isurban = isurban
+    a%tslb = C_LOC(tslb)
+    a%smois = C_LOC(smois)
+    a%sh2o = C_LOC(sh2o)
+    a%dzs = C_LOC(dzs)
+    a%fndsoilw = MERGE(1_C_INT, 0_C_INT, fndsoilw)
+    a%fndsnowh = MERGE(1_C_INT, 0_C_INT, fndsnowh)
+    a%isice = isice
+    a%iswater = iswater
+    a%tsk = C_LOC(tsk)
+    a%isnowxy = C_LOC(isnowxy)
+    a%tvxy = C_LOC(tvxy)
+    a%tgxy = C_LOC(tgxy)
+    a%canicexy = C_LOC(canicexy)
+    a%tmn = C_LOC(tmn)
+    a%xice = C_LOC(xice)
+    a%canliqxy = C_LOC(canliqxy)
+    a%eahxy = C_LOC(eahxy)
+    a%tahxy = C_LOC(tahxy)
+    a%cmxy = C_LOC(cmxy)
+    a%chxy = C_LOC(chxy)
+    a%fwetxy = C_LOC(fwetxy)
+    a%sneqvoxy = C_LOC(sneqvoxy)
+    a%alboldxy = C_LOC(alboldxy)
+    a%qsnowxy = C_LOC(qsnowxy)
+    a%wslakexy = C_LOC(wslakexy)
+    a%zwtxy = C_LOC(zwtxy)
+    a%waxy = C_LOC(waxy)
+    a%wtxy = C_LOC(wtxy)
+    a%tsnoxy = C_LOC(tsnoxy)
+    a%zsnsoxy = C_LOC(zsnsoxy)
+    a%snicexy = C_LOC(snicexy)
+    a%snliqxy = C_LOC(snliqxy)
+    a%lfmassxy = C_LOC(lfmassxy)
+    a%rtmassxy = C_LOC(rtmassxy)
+    a%stmassxy = C_LOC(stmassxy)
+    a%woodxy = C_LOC(woodxy)
+    a%stblcpxy = C_LOC(stblcpxy)
+    a%fastcpxy = C_LOC(fastcpxy)
+    a%xsaixy = C_LOC(xsaixy)
+    a%t2mvxy = C_LOC(t2mvxy)
+    a%t2mbxy = C_LOC(t2mbxy)
+    a%chstarxy = C_LOC(chstarxy)
+    a%nsoil = nsoil
+    a%restart = MERGE(1_C_INT, 0_C_INT, restart)
+    a%allowed_to_read = MERGE(1_C_INT, 0_C_INT, allowed_to_read)
+    a%iopt_run = iopt_run
+    a%ids = ids
+    a%ide = ide
+    a%jds = jds
+    a%jde = jde
+    a%kds = kds
+    a%kde = kde
+    a%ims = ims
+    a%ime = ime
+    a%jms = jms
+    a%jme = jme
+    a%kms = kms
+    a%kme = kme
+    a%its = its
+    a%ite = ite
+    a%jts = jts
+    a%jte = jte
+    a%kts = kts
+    a%kte = kte
+    ! optional groundwater block: absent arguments travel as NULL and the library answers as the reference does
+    ! ('Not enough fields to use groundwater option in Noah-MP') when iopt_run = 5 needs them
+    a%smoiseq = C_NULL_PTR; IF (PRESENT(smoiseq)) a%smoiseq = C_LOC(smoiseq)
+    a%smcwtdxy = C_NULL_PTR; IF (PRESENT(smcwtdxy)) a%smcwtdxy = C_LOC(smcwtdxy)
+    a%rechxy = C_NULL_PTR; IF (PRESENT(rechxy)) a%rechxy = C_LOC(rechxy)
+    a%deeprechxy = C_NULL_PTR; IF (PRESENT(deeprechxy)) a%deeprechxy = C_LOC(deeprechxy)
+    a%areaxy = C_NULL_PTR; IF (PRESENT(areaxy)) a%areaxy = C_LOC(areaxy)
+    a%msftx = C_NULL_PTR; IF (PRESENT(msftx)) a%msftx = C_LOC(msftx)
+    a%msfty = C_NULL_PTR; IF (PRESENT(msfty)) a%msfty = C_LOC(msfty)
+    a%stepwtd = C_NULL_PTR; IF (PRESENT(stepwtd)) a%stepwtd = C_LOC(stepwtd)
+    a%qrfsxy = C_NULL_PTR; IF (PRESENT(qrfsxy)) a%qrfsxy = C_LOC(qrfsxy)
+    a%qspringsxy = C_NULL_PTR; IF (PRESENT(qspringsxy)) a%qspringsxy = C_LOC(qspringsxy)
+    a%qslatxy = C_NULL_PTR; IF (PRESENT(qslatxy)) a%qslatxy = C_LOC(qslatxy)
+    a%fdepthxy = C_NULL_PTR; IF (PRESENT(fdepthxy)) a%fdepthxy = C_LOC(fdepthxy)
+    a%ht = C_NULL_PTR; IF (PRESENT(ht)) a%ht = C_LOC(ht)
+    a%riverbedxy = C_NULL_PTR; IF (PRESENT(riverbedxy)) a%riverbedxy = C_LOC(riverbedxy)
+    a%eqzwt = C_NULL_PTR; IF (PRESENT(eqzwt)) a%eqzwt = C_LOC(eqzwt)
+    a%rivercondxy = C_NULL_PTR; IF (PRESENT(rivercondxy)) a%rivercondxy = C_LOC(rivercondxy)
+    a%pexpxy = C_NULL_PTR; IF (PRESENT(pexpxy)) a%pexpxy = C_LOC(pexpxy)
+    a%dx = 0.0; IF (PRESENT(dx)) a%dx = dx
+    a%dy = 0.0; IF (PRESENT(dy)) a%dy = dy
+    a%wtddt = 0.0; IF (PRESENT(wtddt)) a%wtddt = wtddt
+    a%dt = 0.0; IF (PRESENT(dt)) a%dt = dt
+    rc = noahmp_b200_init(ctx, a)
+    IF (rc == 9) CALL wrf_error_fatal("module_sf_noahlsm.F: lsminit: out of range value of ISLTYP. Is this field in the input?")
+    IF (rc /= 0 .AND. iopt_run == 5) CALL wrf_error_fatal('Not enough fields to use groundwater option in Noah-MP')
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200_init failed")
+  END SUBROUTINE NOAHMP_INIT
 
 END MODULE module_sf_noahmpdrv_b200

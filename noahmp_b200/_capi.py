@@ -175,6 +175,47 @@ def make_wtable_args(arrays, scalars):
     return a
 
 
+# ---- cold start (row f1): noahmp_init_args (NOAHMP_INIT dummy list, noahmpdrv.F90:847-864) ------------------------
+INIT_SPEC = (
+    [("snow", "pf"), ("snowh", "pf"), ("canwat", "pf"), ("isltyp", "pi"), ("ivgtyp", "pi"), ("isurban", "i"),
+     ("tslb", "pf"), ("smois", "pf"), ("sh2o", "pf"), ("dzs", "pf"), ("fndsoilw", "i"), ("fndsnowh", "i"),
+     ("isice", "i"), ("iswater", "i"), ("tsk", "pf"), ("isnowxy", "pi"), ("tvxy", "pf"), ("tgxy", "pf"),
+     ("canicexy", "pf"), ("tmn", "pf"), ("xice", "pf")]
+    + [(n, "pf") for n in ("canliqxy eahxy tahxy cmxy chxy fwetxy sneqvoxy alboldxy qsnowxy wslakexy zwtxy waxy wtxy "
+                           "tsnoxy zsnsoxy snicexy snliqxy lfmassxy rtmassxy stmassxy woodxy stblcpxy fastcpxy xsaixy "
+                           "t2mvxy t2mbxy chstarxy").split()]
+    + [("nsoil", "i"), ("restart", "i"), ("allowed_to_read", "i"), ("iopt_run", "i")]
+    + [(n, "i") for n in _BOUNDS]
+    + [(n, "pf") for n in "smoiseq smcwtdxy rechxy deeprechxy areaxy".split()]
+    + [("dx", "f"), ("dy", "f"), ("msftx", "pf"), ("msfty", "pf"), ("wtddt", "f"), ("stepwtd", "pi"), ("dt", "f")]
+    + [(n, "pf") for n in "qrfsxy qspringsxy qslatxy fdepthxy ht riverbedxy eqzwt rivercondxy pexpxy".split()]
+)
+INIT_GW = ("smoiseq smcwtdxy rechxy deeprechxy areaxy msftx msfty stepwtd qrfsxy qspringsxy qslatxy fdepthxy ht "
+           "riverbedxy eqzwt rivercondxy pexpxy").split()
+INIT_LAYERS = {"tslb": 4, "smois": 4, "sh2o": 4, "smoiseq": 4, "tsnoxy": 3, "snicexy": 3, "snliqxy": 3, "zsnsoxy": 7}
+
+
+class NoahmpInitArgs(C.Structure):
+    _fields_ = [(n, _K[k]) for n, k in INIT_SPEC]
+
+
+def make_init_args(arrays, scalars):
+    """arrays: numpy arrays by NOAHMP_INIT dummy name (groundwater ones may be absent -> NULL); scalars: the rest."""
+    a = NoahmpInitArgs()
+    for n, k in INIT_SPEC:
+        if k in ("i", "f"):
+            setattr(a, n, scalars.get(n, 0))
+        elif n in arrays and arrays[n] is not None:
+            arr = arrays[n]
+            want = np.int32 if k == "pi" else np.float32
+            if arr.dtype != want or not arr.flags["C_CONTIGUOUS"]:
+                raise TypeError(f"{n}: need C-contiguous {want.__name__}, got {arr.dtype}")
+            setattr(a, n, arr.ctypes.data_as(_K[k]))
+        elif n not in INIT_GW and n != "tmn":
+            raise KeyError(n)
+    return a
+
+
 # ---- on-device forcing pipeline (row f2): noahmp_forcing_fields ---------------------------------------------------
 FORCING_FIELDS = "t q u v p lw sw pcp fpar".split()
 

@@ -18,6 +18,7 @@ _pa = C.POINTER(_capi.NoahmpLsmArgs)
 _pt = C.POINTER(_capi.NoahmpTables)
 _ps = C.POINTER(_capi.NoahmpStatus)
 _pw = C.POINTER(_capi.NoahmpWtableArgs)
+_pinit = C.POINTER(_capi.NoahmpInitArgs)
 _pff = C.POINTER(_capi.NoahmpForcingFields)
 _ctx = C.c_void_p
 
@@ -57,6 +58,8 @@ SYMBOLS = {
     "noahmp_b200_forcing_apply": (C.c_int, [_ctx, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                            C.POINTER(C.c_float)]),
     "noahmp_b200_noahmplsm_device_forcing": (C.c_int, [_ctx, _pa, _ps]),
+    "noahmp_b200_init": (C.c_int, [_ctx, _pinit]),
+    "noahmp_b200_sizeof_init_args": (C.c_ulonglong, []),
     "noahmp_b200_wtable": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_wtable_begin": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_wtable_end": (C.c_int, [_ctx, _pw]),

@@ -131,6 +131,41 @@ struct ForcingParams {
   float fraction, sin_declin, cos_declin, hour_frac /* IHOUR + IMINUTE/60 + ISECOND/3600 */, dt, zlvl;
 };
 
+// ---- cold start (nmp_init.cuh): arrays of NOAHMP_INIT in dummy-argument order -----------------------------
+// X(name, layers, io)  io: 1 = input only (uploaded), 3 = updated (uploaded and downloaded)
+#define NMP_INIT_FIELDS(X)                                                                                          \
+  X(snow, 1, 3) X(snowh, 1, 3) X(canwat, 1, 3) X(isltyp, 1, 1) X(ivgtyp, 1, 1) X(tslb, 4, 3) X(smois, 4, 3)          \
+  X(sh2o, 4, 3) X(tsk, 1, 1) X(isnowxy, 1, 3) X(tvxy, 1, 3) X(tgxy, 1, 3) X(canicexy, 1, 3) X(xice, 1, 1)            \
+  X(canliqxy, 1, 3) X(eahxy, 1, 3) X(tahxy, 1, 3) X(cmxy, 1, 3) X(chxy, 1, 3) X(fwetxy, 1, 3) X(sneqvoxy, 1, 3)      \
+  X(alboldxy, 1, 3) X(qsnowxy, 1, 3) X(wslakexy, 1, 3) X(zwtxy, 1, 3) X(waxy, 1, 3) X(wtxy, 1, 3) X(tsnoxy, 3, 3)    \
+  X(zsnsoxy, 7, 3) X(snicexy, 3, 3) X(snliqxy, 3, 3) X(lfmassxy, 1, 3) X(rtmassxy, 1, 3) X(stmassxy, 1, 3)           \
+  X(woodxy, 1, 3) X(stblcpxy, 1, 3) X(fastcpxy, 1, 3) X(xsaixy, 1, 3) X(t2mvxy, 1, 3) X(t2mbxy, 1, 3)                \
+  X(chstarxy, 1, 3)
+// the optional groundwater block (iopt_run = 5)
+#define NMP_INIT_GW_FIELDS(X)                                                                                       \
+  X(smoiseq, 4, 3) X(smcwtdxy, 1, 3) X(rechxy, 1, 3) X(deeprechxy, 1, 3) X(areaxy, 1, 3) X(msftx, 1, 1)              \
+  X(msfty, 1, 1) X(qrfsxy, 1, 3) X(qspringsxy, 1, 3) X(qslatxy, 1, 3) X(fdepthxy, 1, 1) X(ht, 1, 1)                  \
+  X(riverbedxy, 1, 1) X(eqzwt, 1, 1) X(rivercondxy, 1, 1) X(pexpxy, 1, 1)
+enum InitField {
+#define X(nm, nl, io) IF_##nm,
+  NMP_INIT_FIELDS(X) IF_GW0,
+  IF_GW_PREV = IF_GW0 - 1,
+  NMP_INIT_GW_FIELDS(X)
+#undef X
+  NINITF
+};
+struct InitParams {
+  float* f[NINITF];     // grid-order device arrays, Fortran (i,k,j) layout; integer arrays as int32 bit patterns
+  float *kcell, *head;  // LATERALFLOW pass-1 planes (iopt_run = 5)
+  int* err;             // 0, or 1 = ISLTYP < 1, 2 = snow depth is not a number
+  const noahmp_tables* tables;
+  int ni, nj, itf_n, jtf_n;  // tile size; cells with il < itf_n and jl < jtf_n are initialised
+  int ids, ide, jds, jde, its, ite, jts, jte;
+  int isurban, isice, iswater, iopt_run, fndsnowh;
+  float dx, dy, deltat;
+  float dzs[NOAHMP_NSOIL];
+};
+
 // compact-column ranges one launch of the physics covers (a whole tile, or one row chunk of it)
 struct StepRange {
   int land_first, land_count, glac_first, glac_count;

@@ -5,6 +5,7 @@
 #include "nmp_kernels.cuh"
 #include "nmp_groundwater.cuh"
 #include "nmp_forcing.cuh"
+#include "nmp_init.cuh"
 
 const char* nmp_launch_step_parity(const nmpf::StepParams& base, const nmpf::StepRange& r, cudaStream_t stream,
                                        long long* launches) {
@@ -18,3 +19,6 @@ void nmp_launch_wtable_parity(const nmpf::WtParams& w, cudaStream_t stream, long
 void nmp_launch_forcing_parity(const nmpf::ForcingParams& f, cudaStream_t stream, long long* launches) {
   launch_forcing(f, stream, launches);
 }
+
+// cold start (always this build: runs once, rounds as the oracle does)
+void nmp_launch_init(const nmpf::InitParams& p, cudaStream_t stream, long long* launches) { launch_init(p, stream, launches); }

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +31,7 @@ void nmp_launch_wtable_fast(const WtParams& w, cudaStream_t stream, long long* l
 void nmp_launch_wtable_parity(const WtParams& w, cudaStream_t stream, long long* launches, int phase);
 void nmp_launch_forcing_fast(const ForcingParams& f, cudaStream_t stream, long long* launches);
 void nmp_launch_forcing_parity(const ForcingParams& f, cudaStream_t stream, long long* launches);
+void nmp_launch_init(const InitParams& p, cudaStream_t stream, long long* launches);
 
 static thread_local std::string g_last_error;
 static void set_error(const std::string& s) { g_last_error = s; }
@@ -1410,6 +1412,112 @@ int noahmp_b200_noahmplsm_device_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_
 }
 
 long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- cold start (row f1): NOAHMP_INIT on the device --------------------------------------------------------
+struct InitFieldInfo {
+  const char* name;
+  size_t arg_offset;
+  int layers, io;
+};
+static const InitFieldInfo kInitFields[NINITF] = {
+#define X(nm, nl, io) {#nm, offsetof(noahmp_init_args, nm), nl, io},
+    NMP_INIT_FIELDS(X) NMP_INIT_GW_FIELDS(X)
+#undef X
+};
+unsigned long long noahmp_b200_sizeof_init_args(void) { return sizeof(noahmp_init_args); }
+
+int noahmp_b200_init(noahmp_b200_ctx* ctx, const noahmp_init_args* a) {
+  if (!ctx || !a) return NOAHMP_ERR_ARG;
+  if (a->nsoil != NOAHMP_NSOIL) { set_error("init: nsoil must be 4"); return NOAHMP_ERR_ARG; }
+  if (a->restart) return 0;  // IF (.NOT. restart): a restart run takes every field from the restart file
+  CK(cudaSetDevice(ctx->device));
+  const int ni = a->ime - a->ims + 1, nj = a->jme - a->jms + 1;
+  if (ni != ctx->ni || nj != ctx->nj || a->ims != a->its || a->ime != a->ite || a->jms != a->jts || a->jme != a->jte) {
+    set_error("init: the memory extent must be the tile the context was created for (ims=its ... jme=jte)");
+    return NOAHMP_ERR_ARG;
+  }
+  const bool gw = a->iopt_run == 5;
+  auto hp = [&](int f) { return *reinterpret_cast<float* const*>(reinterpret_cast<const char*>(a) + kInitFields[f].arg_offset); };
+  for (int f = 0; f < NINITF; ++f)
+    if ((f < IF_GW0 || gw) && !hp(f)) {
+      set_error(f < IF_GW0 ? std::string("init: missing array ") + kInitFields[f].name
+                           : std::string("Not enough fields to use groundwater option in Noah-MP: ") + kInitFields[f].name);
+      return NOAHMP_ERR_ARG;
+    }
+  if (!a->dzs || (gw && !a->stepwtd)) { set_error("init: dzs / stepwtd missing"); return NOAHMP_ERR_ARG; }
+  if (gw && (a->ids < a->its || a->ide > a->ite + 1 || a->jds < a->jts || a->jde > a->jte + 1)) {
+    // LATERALFLOW would read WTD one cell outside the memory the caller passed
+    set_error("init: groundwater initialisation needs ids>=its, ide<=ite+1, jds>=jts, jde<=jte+1");
+    return NOAHMP_ERR_ARG;
+  }
+  InitParams P{};
+  const size_t plane = (size_t)ni * nj;
+  size_t words = 0;
+  for (int f = 0; f < NINITF; ++f)
+    if (f < IF_GW0 || gw) words += plane * kInitFields[f].layers;
+  if (gw) words += 2 * plane;
+  float* buf = nullptr;
+  int* d_err = nullptr;
+  CK(cudaMalloc(&buf, words * sizeof(float)));
+  auto fail = [&](int rc) { cudaFree(buf); if (d_err) cudaFree(d_err); return rc; };
+  if (cudaMalloc(&d_err, sizeof(int)) != cudaSuccess) { set_error("init: cudaMalloc"); return fail(NOAHMP_ERR_CUDA); }
+  cudaStream_t s = ctx->stream;
+  size_t off = 0;
+  for (int f = 0; f < NINITF; ++f) {
+    if (!(f < IF_GW0 || gw)) continue;
+    P.f[f] = buf + off;
+    const size_t n = plane * kInitFields[f].layers;
+    off += n;
+    pin(ctx, hp(f), n * sizeof(float));
+    if (cudaMemcpyAsync(P.f[f], hp(f), n * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+      set_error(std::string("init: upload of ") + kInitFields[f].name + " failed");
+      return fail(NOAHMP_ERR_CUDA);
+    }
+  }
+  if (gw) { P.kcell = buf + off; P.head = buf + off + plane; }
+  P.err = d_err;
+  P.tables = ctx->d_tables;
+  P.ni = ni; P.nj = nj;
+  P.itf_n = std::min(a->ite, a->ide - 1) - a->its + 1;
+  P.jtf_n = std::min(a->jte, a->jde - 1) - a->jts + 1;
+  P.ids = a->ids; P.ide = a->ide; P.jds = a->jds; P.jde = a->jde;
+  P.its = a->its; P.ite = a->ite; P.jts = a->jts; P.jte = a->jte;
+  P.isurban = a->isurban; P.isice = a->isice; P.iswater = a->iswater; P.iopt_run = a->iopt_run;
+  P.fndsnowh = a->fndsnowh;
+  P.dx = a->dx; P.dy = a->dy; P.deltat = a->wtddt * 60.f;
+  for (int k = 0; k < NOAHMP_NSOIL; ++k) P.dzs[k] = a->dzs[k];
+  int herr = 0;
+  if (cudaMemsetAsync(d_err, 0, sizeof(int), s) != cudaSuccess) return fail(NOAHMP_ERR_CUDA);
+  nmp_launch_init(P, s, &ctx->launches);
+  if (cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    set_error(std::string("init: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(NOAHMP_ERR_CUDA);
+  }
+  if (herr == 1) {
+    set_error("module_sf_noahlsm.F: lsminit: out of range value of ISLTYP. Is this field in the input?");
+    return fail(NOAHMP_ERR_ISLTYP);
+  }
+  if (herr == 2) { set_error("Problem with the logic assigning snow layers."); return fail(NOAHMP_ERR_ARG); }
+  for (int f = 0; f < NINITF; ++f) {
+    if (!(f < IF_GW0 || gw) || !(kInitFields[f].io & 2)) continue;
+    const size_t n = plane * kInitFields[f].layers;
+    if (cudaMemcpyAsync(hp(f), P.f[f], n * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+      set_error(std::string("init: download of ") + kInitFields[f].name + " failed");
+      return fail(NOAHMP_ERR_CUDA);
+    }
+  }
+  if (cudaStreamSynchronize(s) != cudaSuccess) return fail(NOAHMP_ERR_CUDA);
+  if (gw) {
+    // STEPWTD = max(nint(WTDDT*60./DT), 1)   (:1159-1160)
+    const float x = a->wtddt * 60.f / a->dt;
+    const int n = (int)(x >= 0.f ? floorf(x + 0.5f) : -floorf(-x + 0.5f));
+    *a->stepwtd = std::max(n, 1);
+  }
+  // the host arrays changed: a context that had state uploaded must take them again
+  ctx->uploaded = false;
+  return fail(0);
+}
 
 int noahmp_b200_census(const noahmp_b200_ctx* ctx, int64_t counts[4]) {
   if (!ctx || !ctx->classified) return NOAHMP_ERR_ARG;

@@ -16,7 +16,8 @@ MATH_FAST, MATH_PARITY = 0, 1
 ERROR_TEXT = {
     1: "Stop in Noah-MP (ERRSW)", 2: "Energy budget problem in NOAHMP LSM", 3: "Water budget problem in NOAHMP LSM",
     4: "STOP in Noah-MP (emitted longwave <0)", 5: "CRITICAL PROBLEM: HCAN <= ZPD", 6: "STOP in Noah-MP (ZLVL <= ZPD)",
-    7: "REDPRM: table index out of range", 8: "unsupported option value", 100: "CUDA failure", 101: "bad argument",
+    7: "REDPRM: table index out of range", 8: "unsupported option value",
+    9: "lsminit: out of range value of ISLTYP", 100: "CUDA failure", 101: "bad argument",
 }
 
 
@@ -180,6 +181,18 @@ class NoahMP:
         st = _capi.NoahmpStatus()
         self._check(self._L.noahmp_b200_noahmplsm_device_forcing(self._ctx, C.byref(a), C.byref(st)))
         return st
+
+    # ---- cold start (NOAHMP_INIT) ----------------------------------------------------------------------
+    def init(self, arrays, scalars):
+        """CALL NOAHMP_INIT(...): fills the state arrays in place for a cold start (restart=0); the arrays named in
+        _capi.INIT_GW are needed only with iopt_run=5.  Returns STEPWTD (iopt_run=5) or None."""
+        arrays = dict(arrays)
+        step = np.zeros(1, np.int32)
+        if scalars.get("iopt_run") == 5:
+            arrays["stepwtd"] = step
+        a = _capi.make_init_args(arrays, scalars)
+        self._check_rc(self._L.noahmp_b200_init(self._ctx, C.byref(a)))
+        return int(step[0]) if scalars.get("iopt_run") == 5 else None
 
     # ---- opt_run = 5 groundwater (WTABLE_mmf_noahmp) --------------------------------------------------
     def wtable(self, arrays, scalars):

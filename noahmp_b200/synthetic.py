@@ -319,6 +319,26 @@ def _snow_init(swe, snodep, tg, zsoil):
     return isnow, tsno, snice, snliq, zsnso
 
 
+def raw_initial_fields(cfg, st, frc1):
+    """What a cold-start input file provides before NOAHMP_INIT runs: TSK, TSLB, SMOIS, SNOW (mm), SNOWH (m)."""
+    f = np.float32
+    g = st["_g"]
+    nj, ni = g.shape
+    xp = backend()
+    tsk = frc1["t"].astype(np.float32)
+    zsoil = -np.cumsum(DZS).astype(np.float32)
+    R = {"tsk": tsk, "tslb": np.zeros((nj, 4, ni), f), "smois": np.zeros((nj, 4, ni), f)}
+    sm = (0.15 + 0.20 * uniform(xp, g, -1, F_SMOIS)).astype(np.float32)
+    for k in range(4):
+        w = f(np.exp(zsoil[k] / 2.0))  # relax from skin temperature towards TMN with depth
+        R["tslb"][:, k, :] = (st["tmn"] + (tsk - st["tmn"]) * w).astype(np.float32)
+        R["smois"][:, k, :] = sm
+    snodep = np.where(uniform(xp, g, -1, F_SNOW) < cfg.snow_frac, 0.5 + uniform(xp, g, -1, F_SNODEP), 0.0)
+    R["snowh"] = snodep.astype(np.float32)
+    R["snow"] = (f(250.0) * R["snowh"]).astype(np.float32)  # BASELINE.md: SNOW = 250*SNODEP mm
+    return R
+
+
 def cold_start(cfg, st, frc1, tables):
     """Initial state arrays (numpy, Fortran layout as (nj[,k],ni)) for a tile: restated NOAHMP_INIT.
 
@@ -327,27 +347,20 @@ def cold_start(cfg, st, frc1, tables):
     f = np.float32
     g = st["_g"]
     nj, ni = g.shape
-    xp = backend()
     A = {}
     for n in _capi.INOUT_NAMES + _capi.OUT_NAMES:
         A[n] = np.zeros(_capi.array_shape(n, ni, nj), _capi.array_dtype(n))
     veg, soil = st["ivgtyp"], st["isltyp"]
     glac = (veg == ISICE) & (st["xice"] <= 0.0)
-    tsk = frc1["t"].astype(np.float32)
     smcmax = tables["maxsmc"][soil - 1]
     bb = tables["bb"][soil - 1]
     psisat = tables["satpsi"][soil - 1]
     zsoil = -np.cumsum(DZS).astype(np.float32)
-    # soil moisture / temperature profiles
-    sm = (0.15 + 0.20 * uniform(xp, g, -1, F_SMOIS)).astype(np.float32)
-    for k in range(4):
-        w = f(np.exp(zsoil[k] / 2.0))  # relax from skin temperature towards TMN with depth
-        A["tslb"][:, k, :] = (st["tmn"] + (tsk - st["tmn"]) * w).astype(np.float32)
-        A["smois"][:, k, :] = sm
-    # snow
-    snodep = np.where(uniform(xp, g, -1, F_SNOW) < cfg.snow_frac, 0.5 + uniform(xp, g, -1, F_SNODEP), 0.0)
-    snodep = snodep.astype(np.float32)
-    swe = (f(250.0) * snodep).astype(np.float32)  # SNOW = 250*SNODEP mm
+    raw = raw_initial_fields(cfg, st, frc1)
+    tsk = raw["tsk"]
+    A["tslb"][...] = raw["tslb"]
+    A["smois"][...] = raw["smois"]
+    snodep, swe = raw["snowh"], raw["snow"]
     # --- NOAHMP_INIT :1032-1069
     for k in range(4):
         smk, tk = A["smois"][:, k, :], A["tslb"][:, k, :]

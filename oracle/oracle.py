@@ -79,6 +79,17 @@ def wtable(arrays, scalars, tables_struct):
         raise RuntimeError(f"nmo_wtable failed: {rc}")
 
 
+def init(arrays, scalars, tables_struct):
+    """The oracle's NOAHMP_INIT on host arrays (updated in place). Returns (rc, STEPWTD or None)."""
+    arrays = dict(arrays)
+    step = np.zeros(1, np.int32)
+    if scalars.get("iopt_run") == 5:
+        arrays["stepwtd"] = step
+    a = _capi.make_init_args(arrays, scalars)
+    rc = lib().nmo_init(C.byref(a), C.byref(tables_struct))
+    return rc, (int(step[0]) if scalars.get("iopt_run") == 5 else None)
+
+
 def forcing(A, B, lat2d, lon2d, fraction, iday, ihour, iminute, isecond, dt, zlvl=30.0):
     """Oracle of the driver-side forcing preparation. A, B: dicts of the 9 forcing-file fields. Returns
     (list of the 12 forcing planes in NOAHMP_NFORCING order, JULIAN)."""

@@ -26,3 +26,9 @@ def built():
 def tables_usgs():
     from noahmp_b200 import tables
     return tables.default_tables("USGS")
+
+
+@pytest.fixture(scope="session")
+def tables_usgs_struct(tables_usgs):
+    from noahmp_b200 import _capi
+    return _capi.tables_from_dict(tables_usgs)

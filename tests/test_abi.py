@@ -24,6 +24,7 @@ def test_struct_sizes_match_library(built):
     L = _lib.lib()
     assert L.noahmp_b200_sizeof_tables() == C.sizeof(_capi.NoahmpTables)
     assert L.noahmp_b200_sizeof_args() == C.sizeof(_capi.NoahmpLsmArgs)
+    assert L.noahmp_b200_sizeof_init_args() == C.sizeof(_capi.NoahmpInitArgs)
 
 
 def test_no_cpu_fallback(built):
