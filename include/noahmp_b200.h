@@ -308,6 +308,17 @@ int noahmp_b200_wtable_end(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args)
 int noahmp_b200_wtable_halo(noahmp_b200_ctx* ctx, float** kcell, float** head);
 int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
 
+/* ---- output / restart staging --------------------------------------------------
+ * For a context whose state lives in HBM (RESIDENT mode): snapshot the named state fields (comma separated
+ * noahmp_lsm_args member names, or "*" for all INOUT/OUT arrays) as of the latest step, and copy them into the
+ * caller's host arrays in the background while later steps run.  mask_water != 0 writes -1.E33 where
+ * IVGTYP == ISWATER, which is what put_var_2d / put_var_3d do to history output
+ * (driver/module_hrldas_netcdf_io.F90:1950-2052: `where (vegtyp == ISWATER .and. .not. restart_flag)`); pass 0 for
+ * restart files (:612-672 of module_hrldas_noahmp_driver.F90).  The host arrays are valid after _output_wait.
+ * One snapshot in flight at a time (_begin waits for the previous one). */
+int noahmp_b200_output_begin(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args, const char* fields, int mask_water);
+int noahmp_b200_output_wait(noahmp_b200_ctx* ctx);
+
 /* ---- cold start: replaces `CALL NOAHMP_INIT(...)` -------------------------------
  * phys/module_sf_noahmpdrv.F90:847-1179 with SNOW_INIT :1182-1283, GROUNDWATER_INIT :1286-1470 and EQSMOISTURE
  * :1473-1522; call site driver/module_hrldas_noahmp_driver.F90:281-297.  One member per dummy argument, same names,

@@ -311,6 +311,13 @@ MODULE module_sf_noahmpdrv_b200
     FUNCTION noahmp_b200_init(c, args) BIND(C, NAME="noahmp_b200_init") RESULT(rc)
       IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_init_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION noahmp_b200_output_begin(c, args, fields, mask_water) BIND(C, NAME="noahmp_b200_output_begin") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_lsm_args), INTENT(IN) :: args
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: fields(*); INTEGER(C_INT), VALUE :: mask_water; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_output_wait(c) BIND(C, NAME="noahmp_b200_output_wait") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT) :: rc
+    END FUNCTION
   END INTERFACE
 
 CONTAINS
@@ -338,6 +345,22 @@ CONTAINS
     rc = noahmp_b200_sync_host(ctx, last_args)
     IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: sync_host failed")
   END SUBROUTINE noahmp_b200_refresh_host
+
+  !> RESIDENT mode, asynchronous variant of refresh_host: snapshot the state as of the step just taken and copy it
+  !> down while the next steps run.  history = .TRUE. masks water points with -1.E33 (what put_var_2d/3d would do).
+  !> Call noahmp_b200_snapshot_wait() right before the nf90_put_var calls.
+  SUBROUTINE noahmp_b200_snapshot_begin(history)
+    LOGICAL, INTENT(IN) :: history
+    INTEGER(C_INT) :: rc
+    rc = noahmp_b200_output_begin(ctx, last_args, "*"//C_NULL_CHAR, MERGE(1_C_INT, 0_C_INT, history))
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: output_begin failed")
+  END SUBROUTINE noahmp_b200_snapshot_begin
+
+  SUBROUTINE noahmp_b200_snapshot_wait()
+    INTEGER(C_INT) :: rc
+    rc = noahmp_b200_output_wait(ctx)
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: output_wait failed")
+  END SUBROUTINE noahmp_b200_snapshot_wait
 
   SUBROUTINE noahmp_b200_stop()
     CALL noahmp_b200_destroy(ctx)

@@ -59,6 +59,8 @@ SYMBOLS = {
                                            C.POINTER(C.c_float)]),
     "noahmp_b200_noahmplsm_device_forcing": (C.c_int, [_ctx, _pa, _ps]),
     "noahmp_b200_init": (C.c_int, [_ctx, _pinit]),
+    "noahmp_b200_output_begin": (C.c_int, [_ctx, _pa, C.c_char_p, C.c_int]),
+    "noahmp_b200_output_wait": (C.c_int, [_ctx]),
     "noahmp_b200_sizeof_init_args": (C.c_ulonglong, []),
     "noahmp_b200_wtable": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_wtable_begin": (C.c_int, [_ctx, _pw]),

@@ -114,6 +114,13 @@ struct noahmp_b200_ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_k, ev_out, ev_plane;
   cudaEvent_t ev_t0 = nullptr;
+  // output staging (row f3): snapshot buffer and its events
+  float* d_outstage = nullptr;
+  size_t outstage_words = 0;
+  cudaEvent_t ev_outready = nullptr, ev_outdone = nullptr;
+  bool out_pending = false;
+  cudaStream_t last_step_stream = nullptr;  // a caller stream the latest device-side step ran on
+  int iswater = 16;
   bool trace = false;  // NOAHMP_B200_TRACE: print the per-chunk timeline of every RESIDENT-mode call
   // opt_run = 5 groundwater: grid-order planes (see WtPlane) and the haloed KCELL / HEAD planes
   float* d_wt[12] = {};
@@ -513,6 +520,7 @@ noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int
   }
   auto* ctx = new noahmp_b200_ctx();
   ctx->device = device; ctx->ni = ni; ctx->nj = nj; ctx->ncell = (long long)ni * nj;
+  ctx->iswater = tables->iswater;
   const char* env = getenv("NOAHMP_B200_MATH");
   if (env && (!strcmp(env, "parity") || !strcmp(env, "1"))) ctx->math_mode = 1;
   env = getenv("NOAHMP_B200_PIN");
@@ -573,6 +581,9 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   for (auto e : ctx->ev_in) cudaEventDestroy(e);
   for (auto e : ctx->ev_k) cudaEventDestroy(e);
   for (auto e : ctx->ev_out) cudaEventDestroy(e);
+  if (ctx->ev_outready) cudaEventDestroy(ctx->ev_outready);
+  if (ctx->ev_outdone) cudaEventDestroy(ctx->ev_outdone);
+  if (ctx->d_outstage) cudaFree(ctx->d_outstage);
   for (auto e : ctx->ev_plane) if (e) cudaEventDestroy(e);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -643,6 +654,7 @@ int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out) {
 int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt, void* stream) {
   if (!ctx || !ctx->uploaded) { set_error("step_device before upload"); return NOAHMP_ERR_ARG; }
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  ctx->last_step_stream = s;
   if (ctx->sync_mode == NOAHMP_SYNC_RESIDENT && ctx->rebin_interval > 0 && ctx->nclass[CL_LAND] > 0) {
     if (itimestep > 1 && (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
       int nch = ctx->bin_chunks ? ctx->bin_chunks
@@ -986,9 +998,7 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
 
 // Fields (comma separated noahmp_lsm_args member names, "" = none) that every RESIDENT-mode noahmplsm call
 // refreshes in the caller's host arrays, e.g. "tsk,hfx,lh,grdflx"; everything else waits for sync_host().
-int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields) {
-  if (!ctx || !fields) return NOAHMP_ERR_ARG;
-  std::vector<int> list;
+static int parse_fields(const char* fields, std::vector<int>& list) {
   std::string s(fields), tok;
   size_t pos = 0;
   while (pos <= s.size()) {
@@ -1005,7 +1015,105 @@ int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields) {
     if (f == NFIELDS) { set_error("unknown field " + tok); return NOAHMP_ERR_ARG; }
     list.push_back(f);
   }
+  return 0;
+}
+int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields) {
+  if (!ctx || !fields) return NOAHMP_ERR_ARG;
+  std::vector<int> list;
+  int rc = parse_fields(fields, list);
+  if (rc) return rc;
   ctx->fetch = list;
+  return 0;
+}
+
+// ---- output / restart staging (row f3) ---------------------------------------------------------------------
+// out = (mask && IVGTYP == ISWATER) ? -1.E33 : grid, for one field in the Fortran (i,k,j) layout
+__global__ void stage_output_kernel(const float* __restrict__ grid, float* __restrict__ out, const float* __restrict__ ivgtyp_bits,
+                                    int iswater, int mask, int layers, int ni, long long ncell) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const bool water = mask && __float_as_int(ivgtyp_bits[c]) == iswater;
+  const long long i = c % ni, j = c / ni;
+  for (int k = 0; k < layers; ++k) {
+    const long long q = i + (long long)k * ni + j * ni * layers;
+    out[q] = water ? -1.E33f : grid[q];
+  }
+}
+
+int noahmp_b200_output_wait(noahmp_b200_ctx* ctx) {
+  if (!ctx) return NOAHMP_ERR_ARG;
+  if (!ctx->out_pending) return 0;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_outdone));
+  ctx->out_pending = false;
+  return 0;
+}
+
+int noahmp_b200_output_begin(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, const char* fields, int mask_water) {
+  if (!ctx || !a || !fields || !ctx->uploaded) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_bounds(ctx, a);
+  if (rc) return rc;
+  std::vector<int> list;
+  if (!strcmp(fields, "*")) {
+    for (int f = 0; f < NFIELDS; ++f) list.push_back(f);
+  } else if ((rc = parse_fields(fields, list))) {
+    return rc;
+  }
+  if ((rc = noahmp_b200_output_wait(ctx))) return rc;  // one snapshot in flight at a time
+  if (list.empty()) return 0;
+  if (!ctx->s_out) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  if (!ctx->ev_outdone) {
+    CK(cudaEventCreateWithFlags(&ctx->ev_outdone, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_outready, cudaEventDisableTiming));
+  }
+  size_t words = 0;
+  for (int f : list) words += (size_t)ctx->ncell * kFields[f].layers;
+  if (words > ctx->outstage_words) {
+    if (ctx->d_outstage) CK(cudaFree(ctx->d_outstage));
+    ctx->d_outstage = nullptr;
+    ctx->outstage_words = 0;
+    CK(cudaMalloc(&ctx->d_outstage, words * sizeof(float)));
+    ctx->outstage_words = words;
+  }
+  cudaStream_t sk = ctx->stream;
+  if (ctx->last_step_stream && ctx->last_step_stream != sk) {  // order the snapshot after steps on a caller stream
+    CK(cudaEventRecord(ctx->ev_outready, ctx->last_step_stream));
+    CK(cudaStreamWaitEvent(sk, ctx->ev_outready, 0));
+  }
+  const int T = 256;
+  size_t off = 0;
+  for (int f : list) {
+    if ((rc = ensure_grid(ctx, f))) return rc;
+    if (ctx->np > 0) {
+      dim3 grid((unsigned)((ctx->np + T - 1) / T), kFields[f].layers);
+      scatter_kernel<<<grid, T, 0, sk>>>(ctx->d_planes + kSlots.slot[f], ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
+    }
+    stage_output_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, sk>>>(
+        ctx->d_grid[f], ctx->d_outstage + off, ctx->d_stat[ST_IVGTYP], ctx->iswater,
+        // put_var_int writes integer fields unmasked (netcdf_io.F90:1985-2010)
+        (mask_water && strcmp(kFields[f].name, "isnowxy")) ? 1 : 0, kFields[f].layers,
+        ctx->ni, ctx->ncell);
+    ctx->launches += 2;
+    off += (size_t)ctx->ncell * kFields[f].layers;
+  }
+  CK(cudaGetLastError());
+  // the snapshot is complete in stream order; later steps on this stream cannot touch it, and the copies below
+  // run beside them on the download stream
+  CK(cudaEventRecord(ctx->ev_outready, sk));
+  CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_outready, 0));
+  off = 0;
+  for (int f : list) {
+    const size_t n = (size_t)ctx->ncell * kFields[f].layers;
+    pin(ctx, host_ptr(a, f), n * sizeof(float));
+    CK(cudaMemcpyAsync(host_ptr(a, f), ctx->d_outstage + off, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
+    off += n;
+  }
+  CK(cudaEventRecord(ctx->ev_outdone, ctx->s_out));
+  ctx->out_pending = true;
   return 0;
 }
 

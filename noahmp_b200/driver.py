@@ -182,6 +182,19 @@ class NoahMP:
         self._check(self._L.noahmp_b200_noahmplsm_device_forcing(self._ctx, C.byref(a), C.byref(st)))
         return st
 
+    # ---- output / restart staging -----------------------------------------------------------------------
+    def output_begin(self, arrays, scalars, fields="*", mask_water=True):
+        """Snapshot `fields` (list or comma separated names, "*" = all state arrays) as of the latest step and start
+        copying them into `arrays` in the background; water points become -1.E33 when mask_water (history output)."""
+        self._out_args = _capi.make_args(arrays, scalars)  # keep the struct and the arrays alive until output_wait
+        self._out_keep = arrays
+        f = fields if isinstance(fields, str) else ",".join(fields)
+        self._check_rc(self._L.noahmp_b200_output_begin(self._ctx, C.byref(self._out_args), f.encode(), int(bool(mask_water))))
+
+    def output_wait(self):
+        self._check_rc(self._L.noahmp_b200_output_wait(self._ctx))
+        self._out_args = self._out_keep = None
+
     # ---- cold start (NOAHMP_INIT) ----------------------------------------------------------------------
     def init(self, arrays, scalars):
         """CALL NOAHMP_INIT(...): fills the state arrays in place for a cold start (restart=0); the arrays named in

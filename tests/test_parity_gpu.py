@@ -360,3 +360,48 @@ def test_groundwater_step_bitexact(built, tables_usgs, sync):
         assert np.array_equal(w_cpu[n].view(np.int32), w_gpu[n].view(np.int32)), n
     assert np.abs(w_gpu["qslat"]).max() > 0 and w_gpu["qrfs"].max() > 0
     m.close()
+
+
+@pytest.mark.gpu
+def test_output_staging_snapshot(built, tables_usgs):
+    """Row f3: output_begin snapshots the state of the latest step; the copies land while later steps run, history
+    output carries -1.E33 at water points (put_var_2d/3d), restart output the plain values."""
+    import noahmp_b200
+    cfg = _cfg("C4", 160, 120)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    a, b = clone_state(state0), clone_state(state0)
+    m1 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST, sync=noahmp_b200.SYNC_FULL)
+    m2 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_FAST, sync=noahmp_b200.SYNC_RESIDENT)
+    xp = S.backend()
+    at6 = None
+    hist = clone_state(state0)
+    names = ["tsk", "tslb", "snowh", "isnowxy", "zsnsoxy", "hfx"]
+    for step in range(1, 10):
+        frc = S.forcing(xp, cfg, step, st)
+        arr_a, sc = S.args_from(cfg, st, frc, a, step)
+        arr_b, _ = S.args_from(cfg, st, frc, b, step)
+        m1.noahmplsm(arr_a, sc); m2.noahmplsm(arr_b, sc)
+        if step == 6:
+            at6 = clone_state(a)
+            arr_h, _ = S.args_from(cfg, st, frc, hist, step)
+            m2.output_begin(arr_h, sc, names, mask_water=True)  # returns at once; steps 7..9 run over it
+    m2.output_wait()
+    water = st["ivgtyp"] == S.ISWATER
+    assert water.any() and (~water).any()
+    for n in names:
+        x, ref = hist[n], at6[n]
+        w = water if x.ndim == 2 else np.broadcast_to(water[:, None, :], x.shape)
+        if x.dtype == np.float32:
+            assert np.all(x[w] == np.float32(-1.0e33)), n
+            assert np.array_equal(x[~w], ref[~w]), n
+        else:
+            assert np.array_equal(x, ref), n  # put_var_int does not mask
+    assert not np.array_equal(hist["tsk"][~water], a["tsk"][~water])  # the run did move on after the snapshot
+    # restart-style snapshot of everything, unmasked, equals the strict drop-in state after the last step
+    rst = clone_state(state0)
+    arr_r, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 9, st), rst, 9)
+    m2.output_begin(arr_r, sc, "*", mask_water=False)
+    m2.output_wait()
+    rep = diff_report(a, rst)
+    assert not rep, rep
+    m1.close(); m2.close()
