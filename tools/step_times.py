@@ -2,7 +2,7 @@ import sys, os, json, numpy as np, torch
 sys.path.insert(0, os.getcwd())
 import noahmp_b200
 from noahmp_b200 import synthetic as S, tables
-interval=int(sys.argv[1]); ni,nj=2304,1920
+interval=int(sys.argv[1]); NS=int(sys.argv[2]) if len(sys.argv)>2 else 30; ni,nj=2304,1920
 cfg=S.named_config("C3"); cfg.ni,cfg.nj=ni,nj
 td=tables.default_tables("USGS"); xp=S.backend()
 st=S.static_fields(xp,cfg); frc1=S.forcing(xp,cfg,1,st); state=S.cold_start(cfg,st,frc1,td)
@@ -16,12 +16,13 @@ for h in range(4):
     f=S.forcing(xt,cfg,1+h,st_t); pl={k:f[k].contiguous() for k in set(order)-{"vegfra","dz8w"}}
     pl["vegfra"]=st_t["vegfra"].contiguous(); pl["dz8w"]=torch.full((nj,ni),60.0,device=dev); ring.append([pl[k] for k in order])
 torch.cuda.synchronize(); stream=torch.cuda.Stream(device=dev)
-ev=[torch.cuda.Event(enable_timing=True) for _ in range(31)]
+ev=[torch.cuda.Event(enable_timing=True) for _ in range(NS+1)]
 ev[0].record(stream)
-for k in range(30):
+for k in range(NS):
     yr,jul,_=S.clock(cfg,1+k); m.bind_forcing([t.data_ptr() for t in ring[k%4]]); m.step_device(1+k,yr,float(jul),3600.0,stream.cuda_stream); ev[k+1].record(stream)
 torch.cuda.synchronize()
-print("interval",interval,"rebins",m.rebins," ".join("%.2f"%ev[k].elapsed_time(ev[k+1]) for k in range(30)))
+tt=[ev[k].elapsed_time(ev[k+1]) for k in range(NS)]
+print("interval",interval,"rebins",m.rebins,"mean %.3f (after step 4: %.3f)"%(sum(tt)/NS,sum(tt[4:])/(NS-4))," ".join("%.2f"%t for t in tt))
 s=m.status(); print("status code",s.code,"count",s.count, "launches", m.launch_count() if hasattr(m,"launch_count") else None)
 for f in ("tsk","sfcrunoff","zwtxy","hfx"):
     m.fetch(arr,sc,f); a=np.asarray(arr[f],dtype=np.float64); print(f,"mean %.6f min %.4f max %.4f nan %d"%(np.nanmean(a),np.nanmin(a),np.nanmax(a),int(np.isnan(a).sum())))
