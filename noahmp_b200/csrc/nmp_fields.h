@@ -94,6 +94,7 @@ struct StepParams {
   int* err_count;
   int* vege_iters;             // optional per-column VEGE_FLUX pass count (diagnostic), may be NULL
   long long np;                // plane stride (number of active columns)
+  unsigned np4;                // the same in bytes (fits: a tile has < 2^25 cells)
   int first, count;            // compact range this launch covers
   int ni;
   int itimestep, yearlen;

@@ -623,6 +623,7 @@ int noahmp_b200_upload(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
   ctx->base.state = ctx->d_state;
   ctx->base.cell = ctx->d_cell;
   ctx->base.np = ctx->np;
+  ctx->base.np4 = (unsigned)(ctx->np * 4);
   ctx->uploaded = true;
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
