@@ -212,13 +212,13 @@ def main():
     xs, xe, ys, ye = noahmp_b200.tile(cfg.ni, cfg.nj, world, rank)
     ni, nj = xe - xs + 1, ye - ys + 1
 
-    # ---- initial state (host, numpy) and upload: not timed ------------------------------------------------
+    # ---- initial state (cold start on the device) and upload: not timed ------------------------------------------------
     xp = S.backend()
     st = S.static_fields(xp, cfg, xs, xe, ys, ye)
     frc1 = S.forcing(xp, cfg, 1, st)
-    state = S.cold_start(cfg, st, frc1, td)
     math = noahmp_b200.MATH_PARITY if args.math == "parity" else noahmp_b200.MATH_FAST
     model = noahmp_b200.NoahMP(td, ni, nj, device=local, sync=noahmp_b200.SYNC_RESIDENT, math=math)
+    state = S.cold_start_device(model, cfg, st, frc1, xs, ys)  # NOAHMP_INIT through the library (row f1)
     if args.chunks:
         model.set_chunks(args.chunks)
     arr, sc = S.args_from(cfg, st, frc1, state, 1)

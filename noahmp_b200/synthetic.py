@@ -418,6 +418,38 @@ def cold_start(cfg, st, frc1, tables):
     return A
 
 
+def cold_start_device(model, cfg, st, frc1, xs=1, ys=1):
+    """The same initial state through the library's own cold start: raw_initial_fields -> NoahMP.init (NOAHMP_INIT on
+    the GPU) -> the driver's first-step guesses.  iopt_run != 5 (groundwater_fields supplies that state)."""
+    f = np.float32
+    g = st["_g"]
+    nj, ni = g.shape
+    A = {}
+    for n in _capi.INOUT_NAMES + _capi.OUT_NAMES:
+        A[n] = np.zeros(_capi.array_shape(n, ni, nj), _capi.array_dtype(n))
+    raw = raw_initial_fields(cfg, st, frc1)
+    for n in ("tsk", "tslb", "smois", "snow", "snowh"):
+        A[n][...] = raw[n]
+    I = {n: A[n] for n, k in _capi.INIT_SPEC if k in ("pf", "pi") and n in A}
+    I.update(isltyp=st["isltyp"], ivgtyp=st["ivgtyp"], xice=st["xice"], tmn=st["tmn"], dzs=DZS,
+             chstarxy=np.zeros((nj, ni), f))
+    sc = dict(isurban=ISURBAN, isice=ISICE, iswater=ISWATER, fndsoilw=0, fndsnowh=1, nsoil=4, restart=0, allowed_to_read=1,
+              iopt_run=cfg.opts["iopt_run"], dx=1000.0, dy=1000.0, wtddt=30.0, dt=float(cfg.dt),
+              ids=xs, ide=xs + ni, jds=ys, jde=ys + nj, kds=1, kde=2, ims=xs, ime=xs + ni - 1, jms=ys, jme=ys + nj - 1,
+              kms=1, kme=2, its=xs, ite=xs + ni - 1, jts=ys, jte=ys + nj - 1, kts=1, kte=2)
+    model.init(I, sc)
+    A["xlaixy"][...] = 1.0  # the driver takes LAI from the forcing file when present
+    # driver first-step guesses (module_hrldas_noahmp_driver.F90:374-384)
+    A["eahxy"][...] = (frc1["p"] * frc1["qv"]) / (f(0.622) + frc1["qv"])
+    A["tahxy"][...] = frc1["t"]
+    A["chxy"][...] = 0.1
+    A["cmxy"][...] = 0.1
+    A["albedo"][...] = 0.2
+    A["emiss"][...] = 0.95
+    A["qsfc"][...] = frc1["qv"] / (f(1.0) + frc1["qv"])
+    return A
+
+
 def args_from(cfg, st, frc, state, itimestep, nk=2):
     """Assemble (arrays, scalars) for _capi.make_args from static fields, one step's forcing and state."""
     nj, ni = st["ivgtyp"].shape

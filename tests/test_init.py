@@ -196,3 +196,23 @@ def test_gpu_init_errors_and_restart(built, tables_usgs):
     with pytest.raises(noahmp_b200.NoahmpError):
         m.init(clone(A), dict(sc, iopt_run=5))  # groundwater arrays missing
     m.close()
+
+
+@pytest.mark.gpu
+def test_device_cold_start_equals_numpy_cold_start(built, tables_usgs):
+    """bench.py starts from the library's own NOAHMP_INIT; the synthetic cases of the parity tests start from the numpy
+    restatement.  Same state, up to the rounding of x**y in the supercooled-water formula."""
+    cfg = S.named_config("C4")
+    cfg.ni, cfg.nj = 120, 80
+    xp = S.backend()
+    st = S.static_fields(xp, cfg)
+    frc1 = S.forcing(xp, cfg, 1, st)
+    ref = S.cold_start(cfg, st, frc1, tables_usgs)
+    m = _gpu_model(tables_usgs, cfg.ni, cfg.nj)
+    dev = S.cold_start_device(m, cfg, st, frc1)
+    m.close()
+    for n in ref:
+        if n == "sh2o":
+            assert np.allclose(dev[n], ref[n], rtol=2e-6, atol=0), n
+        else:
+            assert np.array_equal(dev[n], ref[n]), n
