@@ -168,7 +168,11 @@ unsigned long long noahmp_b200_sizeof_args(void);
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* Creates a device context on CUDA device `device` for a tile of ni x nj columns. Fails (returns
- * NULL) when no CUDA device is usable: there is no CPU fallback. */
+ * NULL) when no CUDA device is usable: there is no CPU fallback.
+ * Host memory: caller arrays of 4 MiB and more that the step-path calls copy are page-locked (cudaHostRegister) on
+ * first use and remembered by address until noahmp_b200_destroy, as a Fortran driver's arrays live for the whole
+ * run.  A caller that frees or reallocates such arrays while the context exists must create the context with the
+ * environment variable NOAHMP_B200_PIN=0 (pageable copies).  noahmp_b200_init never page-locks. */
 noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int ni, int nj);
 void noahmp_b200_destroy(noahmp_b200_ctx* ctx);
 const char* noahmp_b200_last_error(void);

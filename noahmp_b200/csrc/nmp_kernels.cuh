@@ -206,11 +206,13 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const StepParams& p) {
 // ---- land columns: REDPRM + NOAHMP_SFLX (noahmpdrv.F90:449-547, :681-714) ---------------------------
 template <class O>
 __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __grid_constant__ StepParams p) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  // threads past the end redo the last column and skip the stores, so that every thread of the block reaches
+  // Warps are aligned to 32-column (128-byte) boundaries of the planes whatever the first column of the launch is
+  // (row chunks of the RESIDENT pipeline start anywhere): the launch is shifted down by first % 32 lanes.
+  int t = blockIdx.x * blockDim.x + threadIdx.x - (p.first & 31);
+  // threads outside the range redo a column of it and skip the stores, so that every thread of the block reaches
   // the phase barriers inside NOAHMP_SFLX
-  bool live = t < p.count;
-  if (!live) t = p.count - 1;
+  bool live = t >= 0 && t < p.count;
+  if (!live) t = t < 0 ? 0 : p.count - 1;
   ColumnIO io(p, (long long)p.first + t, live);
   Ctx c;
   init_ctx(c, p);
@@ -328,7 +330,7 @@ void launch_pair(const StepParams& base, const nmpf::StepRange& r, cudaStream_t 
     StepParams p = base;
     p.first = r.land_first;
     p.count = nland;
-    land_kernel<O><<<(nland + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
+    land_kernel<O><<<(nland + (r.land_first & 31) + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
     ++*launches;
   }
   if (nglac > 0) {

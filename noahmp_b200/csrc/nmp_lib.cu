@@ -1577,7 +1577,7 @@ int noahmp_b200_init(noahmp_b200_ctx* ctx, const noahmp_init_args* a) {
     P.f[f] = buf + off;
     const size_t n = plane * kInitFields[f].layers;
     off += n;
-    pin(ctx, hp(f), n * sizeof(float));
+    // no page-locking here: the call runs once, and its arrays need not outlive it
     if (cudaMemcpyAsync(P.f[f], hp(f), n * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) {
       set_error(std::string("init: upload of ") + kInitFields[f].name + " failed");
       return fail(NOAHMP_ERR_CUDA);

@@ -71,11 +71,22 @@ class NoahMP:
             raise NoahmpError(100, self._L.noahmp_b200_last_error().decode())
         self.set_mode(sync)
         self.set_math(math)
+        self._held = {}
+
+    def _hold(self, arrays):
+        """The library page-locks caller arrays of 4 MiB and more and remembers them by address (a Fortran driver's
+        arrays live as long as the run).  numpy would unmap a freed array while it is still registered, so arrays of
+        that size stay referenced until close()."""
+        for v in (arrays.values() if isinstance(arrays, dict) else arrays):
+            if isinstance(v, np.ndarray) and v.nbytes >= (4 << 20):
+                self._held[v.ctypes.data] = v
+        return arrays
 
     def close(self):
         if getattr(self, "_ctx", None):
             self._L.noahmp_b200_destroy(self._ctx)
             self._ctx = None
+            self._held = {}
 
     __del__ = close
 
@@ -93,18 +104,18 @@ class NoahMP:
     # ---- the reference-facing call -------------------------------------------------------------
     def noahmplsm(self, arrays, scalars):
         """CALL noahmplsm(...): updates the INOUT/OUT arrays in place (SYNC_FULL) and returns NoahmpStatus."""
-        a = _capi.make_args(arrays, scalars)
+        a = _capi.make_args(self._hold(arrays), scalars)
         st = _capi.NoahmpStatus()
         self._check(self._L.noahmp_b200_noahmplsm(self._ctx, C.byref(a), C.byref(st)))
         return st
 
     def sync_host(self, arrays, scalars):
-        a = _capi.make_args(arrays, scalars)
+        a = _capi.make_args(self._hold(arrays), scalars)
         self._check(self._L.noahmp_b200_sync_host(self._ctx, C.byref(a)))
 
     # ---- device-resident stepping ----------------------------------------------------------------
     def upload(self, arrays, scalars):
-        a = _capi.make_args(arrays, scalars)
+        a = _capi.make_args(self._hold(arrays), scalars)
         self._check(self._L.noahmp_b200_upload(self._ctx, C.byref(a)))
 
     def device_forcing(self):
@@ -137,7 +148,7 @@ class NoahMP:
         self._check(self._L.noahmp_b200_set_chunks(self._ctx, n))
 
     def fetch(self, arrays, scalars, field):
-        a = _capi.make_args(arrays, scalars)
+        a = _capi.make_args(self._hold(arrays), scalars)
         self._check(self._L.noahmp_b200_fetch(self._ctx, C.byref(a), field.encode()))
 
     def step_device(self, itimestep, yr, julian, dt, stream=None):
@@ -164,7 +175,7 @@ class NoahMP:
     def forcing_upload(self, slot, fields):
         """fields: dict t q u v p lw sw pcp fpar of (nj, ni) float32 arrays = one forcing file; slot 0 = A, 1 = B.
         The copy is asynchronous: keep the arrays alive and unchanged until the next forcing_apply returns."""
-        f = _capi.make_forcing_fields(fields)
+        f = _capi.make_forcing_fields(self._hold(fields))
         self._check_rc(self._L.noahmp_b200_forcing_upload(self._ctx, slot, C.byref(f)))
 
     def forcing_swap(self):
@@ -177,7 +188,7 @@ class NoahMP:
         return j.value
 
     def noahmplsm_device_forcing(self, arrays, scalars):
-        a = _capi.make_args(arrays, scalars)
+        a = _capi.make_args(self._hold(arrays), scalars)
         st = _capi.NoahmpStatus()
         self._check(self._L.noahmp_b200_noahmplsm_device_forcing(self._ctx, C.byref(a), C.byref(st)))
         return st
@@ -186,7 +197,7 @@ class NoahMP:
     def output_begin(self, arrays, scalars, fields="*", mask_water=True):
         """Snapshot `fields` (list or comma separated names, "*" = all state arrays) as of the latest step and start
         copying them into `arrays` in the background; water points become -1.E33 when mask_water (history output)."""
-        self._out_args = _capi.make_args(arrays, scalars)  # keep the struct and the arrays alive until output_wait
+        self._out_args = _capi.make_args(self._hold(arrays), scalars)  # keep the struct and the arrays alive until output_wait
         self._out_keep = arrays
         f = fields if isinstance(fields, str) else ",".join(fields)
         self._check_rc(self._L.noahmp_b200_output_begin(self._ctx, C.byref(self._out_args), f.encode(), int(bool(mask_water))))
@@ -210,15 +221,15 @@ class NoahMP:
     # ---- opt_run = 5 groundwater (WTABLE_mmf_noahmp) --------------------------------------------------
     def wtable(self, arrays, scalars):
         """CALL WTABLE_mmf_noahmp(...) on a tile that needs no halo (single tile = whole domain)."""
-        a = _capi.make_wtable_args(arrays, scalars)
+        a = _capi.make_wtable_args(self._hold(arrays), scalars)
         self._check_rc(self._L.noahmp_b200_wtable(self._ctx, C.byref(a)))
 
     def wtable_begin(self, arrays, scalars):
-        a = _capi.make_wtable_args(arrays, scalars)
+        a = _capi.make_wtable_args(self._hold(arrays), scalars)
         self._check_rc(self._L.noahmp_b200_wtable_begin(self._ctx, C.byref(a)))
 
     def wtable_end(self, arrays, scalars):
-        a = _capi.make_wtable_args(arrays, scalars)
+        a = _capi.make_wtable_args(self._hold(arrays), scalars)
         self._check_rc(self._L.noahmp_b200_wtable_end(self._ctx, C.byref(a)))
 
     def wtable_halo(self):
@@ -228,7 +239,7 @@ class NoahMP:
         return _DevArray(k.value, (self.nj + 2, self.ni + 2)), _DevArray(h.value, (self.nj + 2, self.ni + 2))
 
     def wtable_sync_host(self, arrays, scalars):
-        a = _capi.make_wtable_args(arrays, scalars)
+        a = _capi.make_wtable_args(self._hold(arrays), scalars)
         self._check_rc(self._L.noahmp_b200_wtable_sync_host(self._ctx, C.byref(a)))
 
     def _check_rc(self, rc):
