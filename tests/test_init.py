@@ -216,3 +216,21 @@ def test_device_cold_start_equals_numpy_cold_start(built, tables_usgs):
             assert np.allclose(dev[n], ref[n], rtol=2e-6, atol=0), n
         else:
             assert np.array_equal(dev[n], ref[n]), n
+
+
+def test_oracle_init_is_tile_independent(built, tables_usgs_struct):
+    """Without the groundwater option the cold start is column-local: initialising two half tiles gives what the
+    whole domain gives (the reference's MPI ranks each call NOAHMP_INIT on their own tile)."""
+    _, _, _, A, sc = init_case("C4", 64, 40)
+    whole = clone(A)
+    assert O.init(whole, sc, tables_usgs_struct)[0] == 0
+    nj, h = 40, 24
+    for j0, j1 in ((0, h), (h, nj)):
+        part = {}
+        for n, v in A.items():
+            part[n] = v.copy() if n == "dzs" else np.ascontiguousarray(v[j0:j1])
+        s2 = dict(sc, jds=j0 + 1, jde=j1 + 1, jms=j0 + 1, jme=j1, jts=j0 + 1, jte=j1)
+        assert O.init(part, s2, tables_usgs_struct)[0] == 0
+        for n in INIT_OUT:
+            if n in whole:
+                assert np.array_equal(part[n], whole[n][j0:j1]), n
