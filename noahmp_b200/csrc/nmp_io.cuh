@@ -29,14 +29,22 @@ struct ColumnIO {
     __builtin_assume(__isGlobal(q));
     return q;
   }
-  __device__ float forc(int f) const { return __ldg(p.forc[f] + cell); }
+  // State, forcing and outputs are touched once per step, while the ~440-byte spill frame of the column program is
+  // re-read all the time: the plane accesses bypass L1 allocation (ld.global.L1::no_allocate / st.global.cs) so that
+  // L1 keeps the spill lines and the parameter tables (-7.5 % step time, profiles/r01_notes.md).
+  static __device__ float ldstream(const float* q) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(q));
+    return v;
+  }
+  __device__ float forc(int f) const { return ldstream(p.forc[f] + cell); }
   // static inputs: compact copies (planes PLANE_STATIC0 + f), unit stride also after re-binning
-  __device__ float stat(int f) const { return *at(nmpf::PLANE_STATIC0 + f); }
+  __device__ float stat(int f) const { return ldstream(at(nmpf::PLANE_STATIC0 + f)); }
   __device__ int stati(int f) const { return __float_as_int(stat(f)); }
-  __device__ float ld(int slot) const { return *at(slot); }
-  __device__ int ldi(int slot) const { return __float_as_int(*at(slot)); }
-  __device__ void st(int slot, float v) const { if (on) *at(slot) = v; }
-  __device__ void sti(int slot, int v) const { if (on) *at(slot) = __int_as_float(v); }
+  __device__ float ld(int slot) const { return ldstream(at(slot)); }
+  __device__ int ldi(int slot) const { return __float_as_int(ldstream(at(slot))); }
+  __device__ void st(int slot, float v) const { if (on) __stcs(at(slot), v); }
+  __device__ void sti(int slot, int v) const { if (on) __stcs(at(slot), __int_as_float(v)); }
   // accumulator += v.  Production build: one fire-and-forget RED.ADD.F32 (no load latency in the dependency chain;
   // a column has a single writer, so the sum is the same round-to-nearest add).  Parity build: load-add-store,
   // because red.add.f32 flushes subnormals and the oracle does not.
