@@ -48,6 +48,10 @@ for age in (1, 2, 5, 10, 19):
         "exact count": prev,
         "veg/noveg*4+snow": (prev > 0) * 4 + sn,
         "max of last 2 steps": np.maximum(iters[base], iters[base - 1]) * 4 + sn,
+        "veg/noveg, snow, VEGTYP": ((prev > 0) * 4 + sn) * 32 + st["ivgtyp"].ravel(),
+        "veg/noveg, VEGTYP, snow": ((prev > 0) * 32 + st["ivgtyp"].ravel()) * 4 + sn,
+        "bucket5, snow, VEGTYP": (bucket5(prev) * 4 + sn) * 32 + st["ivgtyp"].ravel(),
+        "veg/noveg, snow, SOILTYP": ((prev > 0) * 4 + sn) * 32 + st["isltyp"].ravel(),
     }
     print(f"key from step {base+1}, evaluated on step {t+1} (age {age}):")
     for name, k in keys.items():
