@@ -102,7 +102,7 @@ struct noahmp_b200_ctx {
   // chunk pipeline of the RESIDENT-mode call
   std::vector<int> h_cell;                 // host copy of the column map (grid order, as classified)
   // column re-binning (divergence control): land columns are physically re-ordered inside each row chunk by
-  // (canopy Newton passes of the previous step, snow-layer count)
+  // (canopy tile computed in the previous step yes/no, snow-layer count)
   int rebin_interval = 20, steps_since_rebin = 0, rebins = 0, bin_chunks = 0;
   bool binned = false;
   float* d_state2 = nullptr;
@@ -756,7 +756,9 @@ __global__ void bin_key_kernel(const float* __restrict__ state, long long np, in
   while (c + 1 < nchunks && n >= chunk_first[c + 1]) ++c;
   const int isnow = __float_as_int(state[(long long)NMP_SLOT(isnowxy) * np + n]);
   const int prev = __float_as_int(state[(long long)PLANE_PREV_ITERS * np + n]);
-  const int pb = prev == 0 ? 0 : (prev <= 6 ? 1 : (prev <= 8 ? 2 : (prev <= 12 ? 3 : 4)));
+  // The number of canopy Newton passes itself is not a useful key: it is unpredictable from one step to the next
+  // (tools/binning_study.py), and finer bins only scatter the column -> cell map that the forcing is read through.
+  const int pb = prev == 0 ? 0 : 1;
   keys[n] = c * 32 + pb * 4 + min(max(-isnow, 0), 3);
   iota[n] = n;
 }
