@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
     ap.add_argument("--grid", type=int, nargs=2, default=None, help="override ni nj (testing only)")
-    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[1536, 1280, 16], help="ni nj steps of the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[1536, 1280, 40], help="ni nj steps of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunks", type=int, default=0, help="row chunks of the e2e pipeline (0 = library default)")
