@@ -854,9 +854,8 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
   const int nk = a->kme - a->kms + 1, kms = a->kms, ni = ctx->ni, nj = ctx->nj;
   const auto t_begin = std::chrono::steady_clock::now();
   if (!ctx->s_in) {
-    const unsigned sf = getenv("NOAHMP_B200_STREAMFLAGS") ? cudaStreamDefault : cudaStreamNonBlocking;
-    CK(cudaStreamCreateWithFlags(&ctx->s_in, sf));
-    CK(cudaStreamCreateWithFlags(&ctx->s_out, sf));
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
   }
   if (!ctx->ev_t0) {
     ctx->trace = getenv("NOAHMP_B200_TRACE") != nullptr;
