@@ -32,10 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_COLUMN_STEP = 824  # 87 words read + 119 words written at the noahmplsm boundary
-# from the ncu --set full capture of the CONUS launch (profiles/r01_ncu_land_quarter_v9_summary.txt (per column, a quarter of CONUS)): DRAM bytes moved and
+# from the ncu --set full capture of the CONUS launch (profiles/r01_ncu_land_conus_v10_summary.txt): DRAM bytes moved and
 # warp-instructions executed per column by land_kernel<dynveg>
-NCU_DRAM_BYTES_PER_COLUMN = (2.213761e9 + 2.162866e9) / 4423680   # profiles/r01_ncu_land_quarter_v9_summary.txt
-NCU_WARP_INSTR_PER_COLUMN = 1207277411 / 4423680
+NCU_DRAM_BYTES_PER_COLUMN = (7.381587e9 + 8.687775e9) / 17694720   # profiles/r01_ncu_land_conus_v10_summary.txt
+NCU_WARP_INSTR_PER_COLUMN = 4832070937 / 17694720
 N_SM, SCHED_PER_SM = 148, 4
 FORCING_ORDER = ["coszin", "t", "qv", "u", "v", "swdown", "glw", "p", "p", "rainbl", "vegfra", "dz8w"]
 
@@ -395,7 +395,7 @@ def main():
             "config": workload_config(cfg, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_COLUMN * ncol if cfg.name == "C3" else None,
-                         "traffic_source": "ncu dram__bytes_read+write of the CONUS launch, profiles/r01_ncu_land_quarter_v9_summary.txt (per column, a quarter of CONUS)",
+                         "traffic_source": "ncu dram__bytes_read+write of the CONUS launch, profiles/r01_ncu_land_conus_v10_summary.txt",
                          "peak_source": peak_src, "kernel": f"land_kernel<{model.variant}>",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLUMN_STEP,
                          "columns_per_launch": ncol, "kernel_ms": mean_ms,
@@ -408,7 +408,7 @@ def main():
                                "peak_source": "measured FFMA issue rate, tools/peaks.cu -> profiles/r01_peaks.json"
                                               if measured_issue else "nominal 148 SM x 4 schedulers x SM clock",
                                "frac": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3) / issue_peak,
-                               "simt_efficiency": 0.773,
+                               "simt_efficiency": 0.772,
                                "source": "instruction count from ncu (profiles/), time and clock measured live"},
             "clocks": clocks, "gpu_launches": launches_all, "census": census, "math": args.math,
         }
