@@ -74,7 +74,15 @@ SYMBOLS = {
 
 def build(force=False):
     """Compile the CUDA extension in-tree (nvcc, sm_100a). Cross-compiles without a GPU."""
-    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s", "-j4"]
+    src = os.path.join(_HERE, "csrc")
+    if not force and os.path.exists(SO_PATH):
+        # a prebuilt library that is newer than every source is used as it is, also when the intermediate objects did
+        # not travel with it (the GPU box receives the .so, not necessarily csrc/build/)
+        deps = [os.path.join(src, f) for f in os.listdir(src) if not os.path.isdir(os.path.join(src, f))]
+        deps.append(os.path.join(os.path.dirname(_HERE), "include", "noahmp_b200.h"))
+        if os.path.getmtime(SO_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return SO_PATH
+    args = ["make", "-C", src, "-s", "-j4"]
     if force:
         args.append("-B")
     subprocess.check_call(args)
