@@ -405,3 +405,54 @@ def test_output_staging_snapshot(built, tables_usgs):
     rep = diff_report(a, rst)
     assert not rep, rep
     m1.close(); m2.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 1), (1, 37), (41, 1), (33, 2)])
+def test_degenerate_tiles_bitexact(built, tables_usgs, shape):
+    """One-cell, one-row and one-column tiles (the thinnest tiles mpp_land_partition can hand to a rank), both
+    synchronisation modes."""
+    import noahmp_b200
+    ni, nj = shape
+    cfg = _cfg("C4", ni, nj)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    s_cpu, s_full, s_res = clone_state(state0), clone_state(state0), clone_state(state0)
+    assert run_oracle(cfg, ts, st, s_cpu, 4, math_mode=1) is None
+    m = _model(tables_usgs, (ni, nj), noahmp_b200.MATH_PARITY)
+    assert run_gpu(m, cfg, st, s_full, 4) is None
+    assert not diff_report(s_cpu, s_full)
+    m.close()
+    m = _model(tables_usgs, (ni, nj), noahmp_b200.MATH_PARITY, sync=noahmp_b200.SYNC_RESIDENT)
+    m.set_chunks(3)
+    assert run_gpu(m, cfg, st, s_res, 4) is None
+    xp = S.backend()
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 4, st), s_res, 4)
+    m.sync_host(arr, sc)
+    assert not diff_report(s_cpu, s_res)
+    m.close()
+
+
+@pytest.mark.gpu
+def test_all_water_tile_is_a_noop_after_the_first_step_fill(built, tables_usgs):
+    """A tile without a single land, glacier or sea-ice column: no physics launch, only the ITIMESTEP==1 fills."""
+    import noahmp_b200
+    cfg = _cfg("C4", 40, 24)
+    ts = _capi.tables_from_dict(tables_usgs)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    st["xland"][...] = 2.0
+    st["xice"][...] = 0.0
+    st["ivgtyp"][...] = S.ISWATER
+    s_cpu, s_gpu, s_res = clone_state(state0), clone_state(state0), clone_state(state0)
+    assert run_oracle(cfg, ts, st, s_cpu, 3, math_mode=1) is None
+    for sync, dst in ((noahmp_b200.SYNC_FULL, s_gpu), (noahmp_b200.SYNC_RESIDENT, s_res)):
+        m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY, sync=sync)
+        assert run_gpu(m, cfg, st, dst, 3) is None
+        assert m.census() == {"land": 0, "glacier": 0, "seaice": 0, "water": cfg.ni * cfg.nj}
+        if sync == noahmp_b200.SYNC_RESIDENT:
+            xp = S.backend()
+            arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 3, st), dst, 3)
+            m.output_begin(arr, sc, "*", mask_water=False)
+            m.output_wait()
+        m.close()
+        assert not diff_report(s_cpu, dst)
