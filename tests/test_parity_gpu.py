@@ -456,3 +456,12 @@ def test_all_water_tile_is_a_noop_after_the_first_step_fill(built, tables_usgs):
             m.output_wait()
         m.close()
         assert not diff_report(s_cpu, dst)
+
+
+@pytest.mark.gpu
+def test_tile_size_limit_is_reported(built, tables_usgs):
+    """A tile of 2^25 cells or more does not fit the 32-bit plane stride: create() refuses it with a message."""
+    import noahmp_b200
+    with pytest.raises(noahmp_b200.NoahmpError) as e:
+        noahmp_b200.NoahMP(tables_usgs, 8192, 4096)
+    assert "2^25" in str(e.value)
