@@ -206,12 +206,13 @@ int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
  * only every output_timestep (:440-565). */
 int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields);
 /* RESIDENT mode runs as a pipeline over `nchunks` row chunks (forcing upload | physics | result download overlap);
- * 0 = automatic. */
+ * 0 = automatic (1 for tiles below 2^20 cells, else 9 with the first and the last chunk half as tall as the others).
+ * Must be set before the first re-binning. */
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
 /* Divergence control (north_star item 4): in RESIDENT mode the land columns are physically re-ordered every
- * `interval` steps (default 20, 0 = never), inside their row chunk, into bins of equal snow-layer count and equal
- * canopy-iteration count of the previous step, so the threads of a block take the same branches and leave the
- * Newton loops together.  Results do not depend on the order; noahmp_b200_column_map returns the current one. */
+ * `interval` steps (default 20, 0 = never), inside their row chunk, into bins of equal snow-layer count and canopy
+ * tile computed / not computed in the previous step, so the threads of a block take the same branches.  Results do
+ * not depend on the order; noahmp_b200_column_map returns the current one. */
 int noahmp_b200_set_rebin(noahmp_b200_ctx* ctx, int interval);
 int noahmp_b200_rebin_count(const noahmp_b200_ctx* ctx);
 /* Refresh ONE caller array (named like the noahmp_lsm_args member, e.g. "tsk") from HBM in RESIDENT mode. */

@@ -1127,7 +1127,8 @@ int noahmp_b200_set_rebin(noahmp_b200_ctx* ctx, int interval) {
 }
 int noahmp_b200_rebin_count(const noahmp_b200_ctx* ctx) { return ctx ? ctx->rebins : 0; }
 
-// Number of row chunks of the RESIDENT-mode pipeline (0 = automatic: 1 below 2^20 cells, else 8).
+// Number of row chunks of the RESIDENT-mode pipeline (0 = automatic: 1 below 2^20 cells, else 9, the first and the
+// last half as tall as the others).
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks) {
   if (!ctx || nchunks < 0 || nchunks > 64) return NOAHMP_ERR_ARG;
   ctx->nchunks = nchunks;
