@@ -724,22 +724,14 @@ CONTAINS
 
   !> Drop-in for NOAHMP_INIT (phys/module_sf_noahmpdrv.F90:847-1179): same name, dummy list and order.  The tables are
   !> those noahmp_b200_start() read; call it after noahmp_b200_start().
-  SUBROUTINE NOAHMP_INIT ( MMINLU, SNOW , SNOWH , CANWAT , ISLTYP ,   IVGTYP, ISURBAN, &
-       TSLB , SMOIS , SH2O , DZS , FNDSOILW , FNDSNOWH ,   ISICE,iswater  ,             &
-       TSK, isnowxy , tvxy     ,tgxy     ,canicexy ,         TMN,     XICE,   &
-       canliqxy ,eahxy    ,tahxy    ,cmxy     ,chxy     ,                     &
-       fwetxy   ,sneqvoxy ,alboldxy ,qsnowxy  ,wslakexy ,zwtxy    ,waxy     , &
-       wtxy     ,tsnoxy   ,zsnsoxy  ,snicexy  ,snliqxy  ,lfmassxy ,rtmassxy , &
-       stmassxy ,woodxy   ,stblcpxy ,fastcpxy , xsaixy   , &
-       t2mvxy   ,t2mbxy   ,chstarxy,            &
-       NSOIL, restart,                 &
-       allowed_to_read , iopt_run,                         &
-       ids,ide, jds,jde, kds,kde,                &
-       ims,ime, jms,jme, kms,kme,                &
-       its,ite, jts,jte, kts,kte,                &
-       smoiseq  ,smcwtdxy ,rechxy   ,deeprechxy, areaxy, dx, dy, msftx, msfty,&
-       wtddt    ,stepwtd  ,dt       ,qrfsxy     ,qspringsxy  , qslatxy    ,  &
-       fdepthxy ,ht     ,riverbedxy ,eqzwt     ,rivercondxy ,pexpxy            )
+  SUBROUTINE NOAHMP_INIT( &
+      MMINLU, SNOW, SNOWH, CANWAT, ISLTYP, IVGTYP, ISURBAN, TSLB, SMOIS, SH2O, DZS, FNDSOILW, FNDSNOWH, &
+      ISICE, ISWATER, TSK, ISNOWXY, TVXY, TGXY, CANICEXY, TMN, XICE, CANLIQXY, EAHXY, TAHXY, CMXY, CHXY, &
+      FWETXY, SNEQVOXY, ALBOLDXY, QSNOWXY, WSLAKEXY, ZWTXY, WAXY, WTXY, TSNOXY, ZSNSOXY, SNICEXY, SNLIQXY, &
+      LFMASSXY, RTMASSXY, STMASSXY, WOODXY, STBLCPXY, FASTCPXY, XSAIXY, T2MVXY, T2MBXY, CHSTARXY, NSOIL, &
+      RESTART, ALLOWED_TO_READ, IOPT_RUN, IDS, IDE, JDS, JDE, KDS, KDE, IMS, IME, JMS, JME, KMS, KME, ITS, &
+      ITE, JTS, JTE, KTS, KTE, SMOISEQ, SMCWTDXY, RECHXY, DEEPRECHXY, AREAXY, DX, DY, MSFTX, MSFTY, WTDDT, &
+      STEPWTD, DT, QRFSXY, QSPRINGSXY, QSLATXY, FDEPTHXY, HT, RIVERBEDXY, EQZWT, RIVERCONDXY, PEXPXY)
     CHARACTER(LEN=*), INTENT(IN) :: MMINLU
     INTEGER, INTENT(IN) :: ids,ide, jds,jde, kds,kde, ims,ime, jms,jme, kms,kme, its,ite, jts,jte, kts,kte
     INTEGER, INTENT(IN) :: NSOIL, ISICE, ISWATER, ISURBAN, iopt_run
