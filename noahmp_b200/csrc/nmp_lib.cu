@@ -765,16 +765,27 @@ __global__ void bin_key_kernel(const float* __restrict__ state, long long np, in
 // new[plane][i] = old[plane][perm[i]] for land columns, plain copy for the other classes; blockIdx.y = plane
 // OUT planes (plane_kind 1) are rewritten for every land column by the step that follows, so only their non-land
 // tail is carried over.
+// One thread moves its column in PERMUTE_GROUP planes: the permutation index is read once per group and the group's
+// gathers are in flight together.
+constexpr int PERMUTE_GROUP = 8;
 __global__ void permute_state_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ perm,
-                                     const unsigned char* __restrict__ plane_kind, long long np, int nland) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                     const unsigned char* __restrict__ plane_kind, long long np, int nland, int nplanes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= np) return;
-  const long long base = (long long)blockIdx.y * np;
-  if (i < nland) {
-    if (plane_kind[blockIdx.y] == 0) dst[base + i] = src[base + (long long)perm[i]];
-  } else {
-    dst[base + i] = src[base + i];
+  const bool land = i < nland;
+  const long long j = land ? (long long)perm[i] : i;
+  const int p0 = blockIdx.y * PERMUTE_GROUP;
+  float v[PERMUTE_GROUP];
+  bool move[PERMUTE_GROUP];
+#pragma unroll
+  for (int g = 0; g < PERMUTE_GROUP; ++g) {
+    const int pl = p0 + g;
+    move[g] = pl < nplanes && (!land || plane_kind[pl] == 0);
+    if (move[g]) v[g] = src[(long long)pl * np + j];
   }
+#pragma unroll
+  for (int g = 0; g < PERMUTE_GROUP; ++g)
+    if (move[g]) dst[(long long)(p0 + g) * np + i] = v[g];
 }
 __global__ void permute_cell_kernel(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ perm,
                                     long long np, int nland) {
@@ -818,8 +829,9 @@ static int rebin(noahmp_b200_ctx* ctx) {
   }
   // stable LSD radix sort: columns of equal key keep their current relative order
   CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
-  dim3 grid((unsigned)((np + T - 1) / T), NPLANES_ALLOC);
-  permute_state_kernel<<<grid, T, 0, s>>>(ctx->d_state, ctx->d_state2, ctx->d_perm, ctx->d_plane_kind, np, nland);
+  dim3 grid((unsigned)((np + T - 1) / T), (NPLANES_ALLOC + PERMUTE_GROUP - 1) / PERMUTE_GROUP);
+  permute_state_kernel<<<grid, T, 0, s>>>(ctx->d_state, ctx->d_state2, ctx->d_perm, ctx->d_plane_kind, np, nland,
+                                          NPLANES_ALLOC);
   permute_cell_kernel<<<(unsigned)((np + T - 1) / T), T, 0, s>>>(ctx->d_cell, ctx->d_cell2, ctx->d_perm, np, nland);
   ctx->launches += 2;
   CK(cudaGetLastError());
