@@ -656,6 +656,8 @@ int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float j
   if (!ctx || !ctx->uploaded) { set_error("step_device before upload"); return NOAHMP_ERR_ARG; }
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   ctx->last_step_stream = s;
+  // a snapshot taken by output_begin on the library's stream must be complete before a caller stream changes the state
+  if (ctx->out_pending && s != ctx->stream) CK(cudaStreamWaitEvent(s, ctx->ev_outready, 0));
   if (ctx->sync_mode == NOAHMP_SYNC_RESIDENT && ctx->rebin_interval > 0 && ctx->nclass[CL_LAND] > 0) {
     if (itimestep > 1 && (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
       int nch = ctx->bin_chunks ? ctx->bin_chunks
