@@ -725,3 +725,20 @@ void ENERGY(Ctx& c, SflxIO& s, SflxLocal& L) {
 }
 
 }  // namespace nmo
+
+// ---- probe for the known-answer test of the two-stream solution (tests/test_oracle.py) -------------------------
+extern "C" void nmo_twostream(const noahmp_tables* tables, int opt_rad, int IB, int IC, int VEGTYP, float COSZ, float VAI,
+                              float FWET, float Tv, float ALBGRD, float ALBGRI, float RHO, float TAU, float FVEG,
+                              float* out /* FAB FRE FTD FTI GDIR */) {
+  using namespace nmo;
+  Ctx c{};
+  c.T = tables;
+  c.O.OPT_RAD = opt_rad;
+  ABand agd, agi, rho, tau, FAB, FRE, FTD, FTI, FREV, FREG;
+  for (int b = 1; b <= 2; ++b) { agd(b) = ALBGRD; agi(b) = ALBGRI; rho(b) = RHO; tau(b) = TAU; }
+  float GDIR = 0.f, BGAP = 0.f, WGAP = 0.f;
+  TWOSTREAM(c, IB, IC, VEGTYP, COSZ, VAI, FWET, Tv, agd, agi, rho, tau, FVEG, FAB, FRE, FTD, FTI, GDIR, FREV, FREG, BGAP,
+            WGAP);
+  out[0] = FAB(IB); out[1] = FRE(IB); out[2] = FTD(IB); out[3] = FTI(IB); out[4] = GDIR;
+}
+

@@ -847,3 +847,25 @@ void PHASECHANGE(Ctx& c, int ISNOW, float DT, const ASnSo& FACT, const ASnSo& DZ
 }
 
 }  // namespace nmo
+
+// ---- scalar probes for known-answer tests (tests/test_oracle.py) ------------------------------------------------
+extern "C" {
+// First pass of SFCDIF1 (ITER = 1: neutral stratification, MOZ = 0): out = {CM, CH, FV, CH2}
+void nmo_sfcdif1_neutral(float ZLVL, float ZPD, float Z0M, float Z0H, float UR, float* out) {
+  nmo::Ctx c{};
+  float MOZ = 0.f, FM = 0.f, FH = 0.f, FM2 = 0.f, FH2 = 0.f, CM = 0.f, CH = 0.f, FV = 0.f, CH2 = 0.f;
+  int MOZSGN = 0;
+  nmo::SFCDIF1(c, 1, 280.f, 1.2f, 0.f, 0.005f, ZLVL, ZPD, Z0M, Z0H, UR, 1.E-6f, MOZ, MOZSGN, FM, FH, FM2, FH2, CM, CH, FV,
+               CH2);
+  out[0] = CM; out[1] = CH; out[2] = FV; out[3] = CH2;
+}
+// FRH2O: liquid water a soil layer keeps below freezing
+float nmo_frh2o(float TKELV, float SMC, float SH2O, float BEXP, float PSISAT, float SMCMAX) {
+  nmo::Ctx c{};
+  c.P.BEXP = BEXP; c.P.PSISAT = PSISAT; c.P.SMCMAX = SMCMAX;
+  float FREE = 0.f;
+  nmo::FRH2O(c, FREE, TKELV, SMC, SH2O);
+  return FREE;
+}
+}
+

@@ -28,6 +28,108 @@ def test_esat_known_answer(O):
     assert 2330.0 < out[0] < 2345.0
 
 
+@pytest.mark.parametrize("zlvl,zpd,z0m,z0h,ur", [(30.0, 0.0, 0.01, 0.01, 5.0), (30.0, 13.0, 1.1, 1.1, 3.0),
+                                                  (10.0, 0.65, 0.06, 0.006, 8.0)])
+def test_sfcdif1_neutral_pass_is_the_log_law(O, zlvl, zpd, z0m, z0h, ur):
+    """First pass of SFCDIF1 (no stability correction): the textbook neutral drag laws
+    CM = k^2 / ln((z-d)/z0m)^2,  CH = k^2 / (ln((z-d)/z0m) ln((z-d)/z0h)),  u* = U sqrt(CM)."""
+    L = O.lib()
+    L.nmo_sfcdif1_neutral.argtypes = [C.c_float] * 5 + [C.POINTER(C.c_float)]
+    out = (C.c_float * 4)()
+    L.nmo_sfcdif1_neutral(zlvl, zpd, z0m, z0h, ur, out)
+    k = 0.40
+    lm, lh = np.log((zlvl - zpd) / z0m), np.log((zlvl - zpd) / z0h)
+    assert out[0] == pytest.approx(k * k / lm ** 2, rel=2e-6)
+    assert out[1] == pytest.approx(k * k / (lm * lh), rel=2e-6)
+    assert out[2] == pytest.approx(ur * k / lm, rel=2e-6)
+    # the 2-m exchange coefficient: k u* / ln((2+z0h)/z0h)
+    assert out[3] == pytest.approx(k * (ur * k / lm) / np.log((2.0 + z0h) / z0h), rel=2e-6)
+
+
+@pytest.mark.parametrize("t,smc,bexp,psisat,smcmax", [(268.0, 0.30, 5.33, 0.3548, 0.439), (272.5, 0.42, 4.74, 0.1413, 0.434),
+                                                       (255.0, 0.20, 10.39, 0.4677, 0.468), (263.0, 0.35, 2.79, 0.0692, 0.339)])
+def test_frh2o_solves_the_freezing_point_depression(O, t, smc, bexp, psisat, smcmax):
+    """FRH2O (Koren et al. 1999): below freezing the liquid water left in the soil is the root of
+    ln[(psisat g / Lf) (1 + 8 ice)^2 (smcmax / liq)^b] = ln[-(T - T0) / T], found here independently by bisection in
+    fp64; the routine stops its Newton iteration at |d ice| <= 0.005.  At and above freezing all water is liquid."""
+    L = O.lib()
+    L.nmo_frh2o.argtypes = [C.c_float] * 6
+    L.nmo_frh2o.restype = C.c_float
+    free = L.nmo_frh2o(t, smc, smc, bexp, psisat, smcmax)
+    g, lf, t0, ck = 9.80616, 0.3336e6, 273.16, 8.0
+    bx = min(bexp, 5.5)
+
+    def resid(ice):
+        return (np.log((psisat * g / lf) * (1.0 + ck * ice) ** 2 * (smcmax / (smc - ice)) ** bx) - np.log(-(t - t0) / t))
+    lo, hi = 0.0, smc - 0.02
+    if resid(lo) * resid(hi) > 0:  # no root inside: the routine clamps to the nearer end
+        exact = lo if abs(resid(lo)) < abs(resid(hi)) else hi
+    else:
+        for _ in range(80):
+            mid = 0.5 * (lo + hi)
+            if resid(lo) * resid(mid) <= 0:
+                hi = mid
+            else:
+                lo = mid
+        exact = 0.5 * (lo + hi)
+    assert abs((smc - free) - exact) <= 0.006
+    assert 0.0 < free <= smc
+    assert L.nmo_frh2o(273.2, smc, smc, bexp, psisat, smcmax) == np.float32(smc)
+    # colder soil keeps less liquid water
+    assert L.nmo_frh2o(t - 5.0, smc, smc, bexp, psisat, smcmax) <= free + 1e-6
+
+
+@pytest.mark.parametrize("ic", [0, 1])
+@pytest.mark.parametrize("vegtyp,cosz,vai,rho,tau,alb", [(2, 0.8, 3.0, 0.11, 0.07, 0.15), (14, 0.3, 1.2, 0.07, 0.05, 0.6),
+                                                         (7, 0.55, 6.0, 0.45, 0.34, 0.25), (11, 0.05, 0.4, 0.10, 0.10, 0.9)])
+def test_twostream_closed_form_solves_the_two_stream_equations(O, tables_usgs, ic, vegtyp, cosz, vai, rho, tau, alb):
+    """TWOSTREAM (noahmplsm.F90:2711-2957) evaluates the closed-form solution (coefficients H1..H10) of the canopy
+    two-stream equations of Dickinson / Sellers.  Independent check: integrate the same boundary-value problem
+      -mu dIup/dx + b Iup - c Idn = d exp(-K x),    mu dIdn/dx + b Idn - c Iup = f exp(-K x),   0 <= x <= VAI,
+    numerically in fp64 (scipy.solve_bvp) and compare albedo and transmitted diffuse flux."""
+    from scipy.integrate import solve_bvp
+    ts = _capi.tables_from_dict(tables_usgs)
+    L = O.lib()
+    L.nmo_twostream.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_float] * 9 + [C.POINTER(C.c_float)]
+    out = (C.c_float * 5)()
+    L.nmo_twostream(C.addressof(ts), 2, 1, ic, vegtyp, cosz, vai, 0.0, 290.0, alb, alb, rho, tau, 1.0, out)
+    fab, fre, ftd, fti, gdir = (float(v) for v in out)
+    # coefficients of the equations (CLM technical note, section 3.1)
+    mu = max(0.001, cosz)
+    chil = min(max(float(tables_usgs["xl"][vegtyp - 1]), -0.4), 0.6)
+    if abs(chil) <= 0.01:
+        chil = 0.01
+    phi1 = 0.5 - 0.633 * chil - 0.330 * chil * chil
+    phi2 = 0.877 * (1.0 - 2.0 * phi1)
+    g = phi1 + phi2 * mu
+    K = g / mu
+    avmu = (1.0 - phi1 / phi2 * np.log((phi1 + phi2) / phi1)) / phi2
+    om = rho + tau
+    asu = 0.5 * om * g / (g + phi2 * mu) * (1.0 - phi1 * mu / (g + phi2 * mu) * np.log((phi1 * mu + g + phi2 * mu) / (phi1 * mu)))
+    beta0 = (1.0 + avmu * K) / (om * avmu * K) * asu
+    beta = 0.5 * (rho + tau + (rho - tau) * ((1.0 + chil) / 2.0) ** 2) / om
+    b, c = 1.0 - om + om * beta, om * beta
+    d, f = (avmu * K * om * beta0, avmu * K * om * (1.0 - beta0)) if ic == 0 else (0.0, 0.0)
+    assert gdir == pytest.approx(g, rel=1e-6)
+
+    def rhs(x, y):
+        e = np.exp(-K * x)
+        return np.vstack([(b * y[0] - c * y[1] - d * e) / avmu, (-b * y[1] + c * y[0] + f * e) / avmu])
+
+    def bc(ya, yb):
+        if ic == 0:
+            return np.array([ya[1], yb[0] - alb * (yb[1] + np.exp(-K * vai))])
+        return np.array([ya[1] - 1.0, yb[0] - alb * yb[1]])
+    x = np.linspace(0.0, vai, 400)
+    sol = solve_bvp(rhs, bc, x, np.zeros((2, x.size)) + 0.1, tol=1e-10, max_nodes=200000)
+    assert sol.success
+    assert fre == pytest.approx(sol.y[0, 0], abs=1e-4)  # fp32 closed form with cancellations vs fp64 integration
+    assert fti == pytest.approx(sol.y[1, -1], abs=1e-4)
+    assert ftd == pytest.approx(np.exp(-K * vai) if ic == 0 else 0.0, abs=1e-6)
+    # what is neither reflected nor absorbed by the ground is absorbed by the canopy
+    assert fab == pytest.approx(1.0 - fre - (1.0 - alb) * (ftd + fti), abs=1e-6) and -1e-6 <= fab <= 1.0
+
+
 @pytest.mark.parametrize("n", [4, 5, 6, 7])
 def test_rosr12_matches_dense_solve(O, n):
     """ROSR12 (noahmplsm.F90:5979-6036) against numpy's dense solver on diagonally dominant systems."""
