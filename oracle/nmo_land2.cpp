@@ -859,6 +859,18 @@ void nmo_sfcdif1_neutral(float ZLVL, float ZPD, float Z0M, float Z0H, float UR, 
                CH2);
   out[0] = CM; out[1] = CH; out[2] = FV; out[3] = CH2;
 }
+// TSNOSOI: one implicit heat-diffusion step of the snow/soil column; arrays are the (-2:4) layers, element IZ + 2
+void nmo_tsnosoi(int opt_stc, int opt_tbot, int ISNOW, float TBOT, const float* ZSNSO, float SSOIL, const float* DF,
+                 const float* HCPCT, float ZBOT, float DT, float SNOWH, float* STC) {
+  using namespace nmo;
+  Ctx c{};
+  c.O.OPT_STC = opt_stc;
+  c.O.OPT_TBOT = opt_tbot;
+  ASnSo z, df, hc, dz, stc;
+  for (int k = -2; k <= NSOIL; ++k) { z(k) = ZSNSO[k + 2]; df(k) = DF[k + 2]; hc(k) = HCPCT[k + 2]; stc(k) = STC[k + 2]; dz(k) = 0.f; }
+  TSNOSOI(c, 0, ISNOW, 1, TBOT, z, SSOIL, df, hc, ZBOT, 0.f, DT, SNOWH, dz, 0.f, stc);
+  for (int k = -2; k <= NSOIL; ++k) STC[k + 2] = stc(k);
+}
 // FRH2O: liquid water a soil layer keeps below freezing
 float nmo_frh2o(float TKELV, float SMC, float SH2O, float BEXP, float PSISAT, float SMCMAX) {
   nmo::Ctx c{};

@@ -130,6 +130,45 @@ def test_twostream_closed_form_solves_the_two_stream_equations(O, tables_usgs, i
     assert fab == pytest.approx(1.0 - fre - (1.0 - alb) * (ftd + fti), abs=1e-6) and -1e-6 <= fab <= 1.0
 
 
+@pytest.mark.parametrize("isnow", [0, -2, -3])
+@pytest.mark.parametrize("opt_tbot", [1, 2])
+def test_tsnosoi_conserves_heat(O, isnow, opt_tbot):
+    """One TSNOSOI step (HRT + HSTEP, noahmplsm.F90:5711-5977) is a conservative implicit diffusion step: the heat
+    content of the snow/soil column changes by DT * (ground heat flux in at the top + flux through the bottom), the
+    bottom flux being zero (opt_tbot=1) or the explicit -DF (T_N - TBOT) / (z_N - ZBOT) of opt_tbot=2.  A uniform
+    column with no flux stays as it is."""
+    L = O.lib()
+    pf = C.POINTER(C.c_float)
+    L.nmo_tsnosoi.argtypes = [C.c_int] * 3 + [C.c_float, pf, C.c_float, pf, pf, C.c_float, C.c_float, C.c_float, pf]
+    f32 = np.float32
+    dzsnow = {0: [], -2: [0.06, 0.11], -3: [0.05, 0.20, 0.31]}[isnow]
+    dzs = np.array(dzsnow + [0.1, 0.3, 0.6, 1.0], np.float64)
+    n = dzs.size
+    # ZSNSO is the depth of every layer bottom below the snow surface (negative downward)
+    z = np.zeros(7, f32); z[7 - n:] = -np.cumsum(dzs)
+    rng = np.random.default_rng(5 + isnow)
+    df = np.zeros(7, f32); df[7 - n:] = rng.uniform(0.1, 2.5, n)
+    hc = np.zeros(7, f32); hc[7 - n:] = rng.uniform(0.5e6, 3.0e6, n)
+    stc0 = np.zeros(7, f32); stc0[7 - n:] = rng.uniform(255.0, 285.0, n)
+    snowh, zbot, tbot, ssoil, dt = f32(sum(dzsnow)), f32(-8.0), f32(279.0), f32(37.5), f32(1800.0)
+    stc = stc0.copy()
+    L.nmo_tsnosoi(1, opt_tbot, isnow, tbot, z.ctypes.data_as(pf), ssoil, df.ctypes.data_as(pf), hc.ctypes.data_as(pf),
+                  zbot, dt, snowh, stc.ctypes.data_as(pf))
+    dh = float(np.sum(hc[7 - n:].astype(np.float64) * dzs * (stc[7 - n:].astype(np.float64) - stc0[7 - n:])))
+    bot = 0.0
+    if opt_tbot == 2:
+        zmid = 0.5 * (float(z[5]) + float(z[6]))
+        bot = -float(df[6]) * (float(stc0[6]) - float(tbot)) / (zmid - (float(zbot) - float(snowh)))
+    want = float(dt) * (float(ssoil) + bot)
+    assert dh == pytest.approx(want, rel=2e-4, abs=50.0)   # J/m2; fp32 tridiagonal solve
+    assert np.all(stc[:7 - n] == 0.0)
+    # no gradients, no fluxes: nothing moves
+    flat = np.zeros(7, f32); flat[7 - n:] = 271.5
+    L.nmo_tsnosoi(1, 2, isnow, f32(271.5), z.ctypes.data_as(pf), f32(0.0), df.ctypes.data_as(pf), hc.ctypes.data_as(pf), zbot,
+                  dt, snowh, flat.ctypes.data_as(pf))
+    assert np.allclose(flat[7 - n:], 271.5, atol=2e-4)
+
+
 @pytest.mark.parametrize("n", [4, 5, 6, 7])
 def test_rosr12_matches_dense_solve(O, n):
     """ROSR12 (noahmplsm.F90:5979-6036) against numpy's dense solver on diagonally dominant systems."""
