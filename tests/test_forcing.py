@@ -42,6 +42,28 @@ def test_calc_declin_matches_numpy_restatement(built, tables_usgs):
         assert np.array_equal(out[10], A["fpar"] * np.float32(100.0))
 
 
+def test_calc_declin_astronomical_known_answers(built, tables_usgs):
+    """Where the sun is overhead at local noon the cosine of the zenith angle is 1: on the June solstice at the Tropic
+    of Cancer (declination +23.44 deg), on the December solstice at the Tropic of Capricorn, at the equinoxes on the
+    equator; and at the equator at local midnight the sun is at the nadir.  The driver's formula for the declination is
+    good to a few tenths of a degree, i.e. 1 - cosz < 1e-3."""
+    from oracle import oracle as O
+    cfg = S.named_config("C1")
+    _, st, _ = make_case(cfg, tables_usgs)
+    A, B = _files(cfg, st, (1, 4))
+    lat = np.zeros_like(st["xlatin"]); lon = np.zeros_like(st["xlong"])
+    O.set_math_mode(0)
+    cases = [(172, 23.44, 12, 1.0), (355, -23.44, 12, 1.0), (80, 0.0, 12, 1.0), (266, 0.0, 12, 1.0), (80, 0.0, 0, -1.0)]
+    for iday, la, hour, want in cases:
+        lat[...] = la
+        out, _ = O.forcing(A, B, lat, lon, 1.0, iday, hour, 0, 0, cfg.dt)
+        assert abs(float(out[0][0, 0]) - want) < 1.5e-3, (iday, la, hour, float(out[0][0, 0]))
+    # 90 degrees of longitude = 6 hours of local time: sunrise/sunset geometry at the equinox on the equator
+    lat[...] = 0.0; lon[...] = 90.0
+    out, _ = O.forcing(A, B, lat, lon, 1.0, 80, 12, 0, 0, cfg.dt)
+    assert abs(float(out[0][0, 0])) < 2e-2
+
+
 def test_interpolation_weights(built, tables_usgs):
     from oracle import oracle as O
     cfg = S.named_config("C1")
