@@ -871,6 +871,26 @@ void nmo_tsnosoi(int opt_stc, int opt_tbot, int ISNOW, float TBOT, const float* 
   TSNOSOI(c, 0, ISNOW, 1, TBOT, z, SSOIL, df, hc, ZBOT, 0.f, DT, SNOWH, dz, 0.f, stc);
   for (int k = -2; k <= NSOIL; ++k) STC[k + 2] = stc(k);
 }
+// PHASECHANGE on a land column; (-2:4) arrays as element IZ + 2, snow arrays (-2:0) likewise, soil arrays (1:4) as K - 1
+void nmo_phasechange(int opt_frz, int ISNOW, float DT, const float* FACT, const float* DZSNSO, float* STC, float* SNICE,
+                     float* SNLIQ, float* SNEQV, float* SNOWH, float* SMC, float* SH2O, float BEXP, float PSISAT,
+                     float SMCMAX, float* QMELT, int* IMELT, float* PONDING) {
+  using namespace nmo;
+  Ctx c{};
+  c.O.OPT_FRZ = opt_frz;
+  c.P.BEXP = BEXP; c.P.PSISAT = PSISAT; c.P.SMCMAX = SMCMAX;
+  ASnSo fact, dz, hc, stc;
+  ASnow ice, liq;
+  ASoil smc, sh2o;
+  IA<-NSNOW + 1, NSOIL> im;
+  for (int k = -2; k <= NSOIL; ++k) { fact(k) = FACT[k + 2]; dz(k) = DZSNSO[k + 2]; hc(k) = 0.f; stc(k) = STC[k + 2]; im(k) = 0; }
+  for (int k = -2; k <= 0; ++k) { ice(k) = SNICE[k + 2]; liq(k) = SNLIQ[k + 2]; }
+  for (int k = 1; k <= NSOIL; ++k) { smc(k) = SMC[k - 1]; sh2o(k) = SH2O[k - 1]; }
+  PHASECHANGE(c, ISNOW, DT, fact, dz, hc, 1, stc, ice, liq, *SNEQV, *SNOWH, smc, sh2o, *QMELT, im, *PONDING);
+  for (int k = -2; k <= NSOIL; ++k) { STC[k + 2] = stc(k); IMELT[k + 2] = im(k); }
+  for (int k = -2; k <= 0; ++k) { SNICE[k + 2] = ice(k); SNLIQ[k + 2] = liq(k); }
+  for (int k = 1; k <= NSOIL; ++k) { SMC[k - 1] = smc(k); SH2O[k - 1] = sh2o(k); }
+}
 // FRH2O: liquid water a soil layer keeps below freezing
 float nmo_frh2o(float TKELV, float SMC, float SH2O, float BEXP, float PSISAT, float SMCMAX) {
   nmo::Ctx c{};

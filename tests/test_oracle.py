@@ -169,6 +169,49 @@ def test_tsnosoi_conserves_heat(O, isnow, opt_tbot):
     assert np.allclose(flat[7 - n:], 271.5, atol=2e-4)
 
 
+@pytest.mark.parametrize("opt_frz", [1, 2])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_phasechange_trades_latent_for_sensible_heat_exactly(O, opt_frz, seed):
+    """PHASECHANGE (noahmplsm.F90:6039-6245) on a snow-free soil column: water mass per layer is unchanged, liquid water
+    stays within [0, SMC], and in every layer the sensible heat that disappears is the latent heat of the ice that
+    melts:  C dz (T_new - T_old) = Lf (ice_new - ice_old),  with C dz = DT / FACT."""
+    L = O.lib()
+    pf, pi = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.nmo_phasechange.argtypes = [C.c_int, C.c_int, C.c_float, pf, pf, pf, pf, pf, pf, pf, pf, pf, C.c_float, C.c_float,
+                                  C.c_float, pf, pi, pf]
+    f32 = np.float32
+    rng = np.random.default_rng(seed)
+    dz = np.array([0, 0, 0, 0.1, 0.3, 0.6, 1.0], f32)
+    hcap = rng.uniform(1.2e6, 3.0e6, 7).astype(f32)
+    dt = f32(1800.0)
+    fact = np.zeros(7, f32); fact[3:] = dt / (hcap[3:] * dz[3:])
+    stc0 = np.zeros(7, f32); stc0[3:] = rng.uniform(271.0, 275.5, 4)
+    smc0 = rng.uniform(0.15, 0.42, 4).astype(f32)
+    sh2o0 = (smc0 * rng.uniform(0.2, 1.0, 4)).astype(f32)
+    stc, smc, sh2o = stc0.copy(), smc0.copy(), sh2o0.copy()
+    snice, snliq = np.zeros(3, f32), np.zeros(3, f32)
+    sneqv, snowh, qmelt, ponding = (C.c_float(0.0) for _ in range(4))
+    imelt = np.zeros(7, np.int32)
+    L.nmo_phasechange(opt_frz, 0, dt, fact.ctypes.data_as(pf), dz.ctypes.data_as(pf), stc.ctypes.data_as(pf),
+                      snice.ctypes.data_as(pf), snliq.ctypes.data_as(pf), C.byref(sneqv), C.byref(snowh),
+                      smc.ctypes.data_as(pf), sh2o.ctypes.data_as(pf), 5.33, 0.3548, 0.439, C.byref(qmelt),
+                      imelt.ctypes.data_as(pi), C.byref(ponding))
+    assert np.allclose(smc, smc0, rtol=3e-7, atol=0)           # total water of a layer does not change
+    assert np.all(sh2o >= 0.0) and np.all(sh2o <= smc * (1 + 1e-6))
+    ice0 = (smc0.astype(np.float64) - sh2o0) * dz[3:] * 1000.0   # kg/m2
+    ice1 = (smc.astype(np.float64) - sh2o) * dz[3:] * 1000.0
+    sensible = hcap[3:].astype(np.float64) * dz[3:] * (stc[3:].astype(np.float64) - stc0[3:])
+    latent = 0.3336e6 * (ice1 - ice0)
+    assert np.allclose(sensible, latent, rtol=2e-3, atol=300.0), (sensible, latent)   # J/m2, fp32 column
+    moved = np.abs(ice1 - ice0) > 1e-2  # kg/m2; below that it is the fp32 round trip through layer masses
+    assert moved.any()
+    assert np.all(imelt[3:][moved] > 0)
+    # melting needs T >= TFRZ, freezing T < TFRZ
+    assert np.all(stc0[3:][(ice1 - ice0) < -1e-2] >= np.float32(273.16))
+    assert np.all(stc0[3:][(ice1 - ice0) > 1e-2] < np.float32(273.16))
+    assert qmelt.value == 0.0 and ponding.value == 0.0
+
+
 @pytest.mark.parametrize("n", [4, 5, 6, 7])
 def test_rosr12_matches_dense_solve(O, n):
     """ROSR12 (noahmplsm.F90:5979-6036) against numpy's dense solver on diagonally dominant systems."""
