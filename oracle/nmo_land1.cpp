@@ -726,6 +726,16 @@ void ENERGY(Ctx& c, SflxIO& s, SflxLocal& L) {
 
 }  // namespace nmo
 
+// TDFCND probe: soil thermal conductivity for given total / liquid water, porosity and quartz content
+extern "C" float nmo_tdfcnd(float SMC, float SH2O, float SMCMAX, float QUARTZ) {
+  nmo::Ctx c{};
+  c.P.SMCMAX = SMCMAX;
+  c.P.QUARTZ = QUARTZ;
+  float DF = 0.f;
+  nmo::TDFCND(c, DF, SMC, SH2O);
+  return DF;
+}
+
 // ---- probe for the known-answer test of the two-stream solution (tests/test_oracle.py) -------------------------
 extern "C" void nmo_twostream(const noahmp_tables* tables, int opt_rad, int IB, int IC, int VEGTYP, float COSZ, float VAI,
                               float FWET, float Tv, float ALBGRD, float ALBGRI, float RHO, float TAU, float FVEG,

@@ -79,6 +79,43 @@ def test_frh2o_solves_the_freezing_point_depression(O, t, smc, bexp, psisat, smc
     assert L.nmo_frh2o(t - 5.0, smc, smc, bexp, psisat, smcmax) <= free + 1e-6
 
 
+def test_esat_against_the_magnus_formula(O):
+    """Saturation vapour pressure over water and over ice between -40 and +40 C: within 0.6 % of the Magnus /
+    Alduchov-Eskridge formulas (an independent fit of the same physical curve)."""
+    out = (C.c_float * 4)()
+    for t in np.arange(-40.0, 40.1, 5.0):
+        O.lib().nmo_esat(C.c_float(t), out)
+        ew = 610.94 * np.exp(17.625 * t / (t + 243.04))
+        assert out[0] == pytest.approx(ew, rel=6e-3), t
+        if t <= 0.0:
+            ei = 611.21 * np.exp(22.587 * t / (t + 273.86))
+            assert out[1] == pytest.approx(ei, rel=6e-3), t
+        # d(es)/dT is a separate polynomial fit of the slope: within 1.5 % of a central difference of the first
+        O.lib().nmo_esat(C.c_float(t + 0.5), out); hi = out[0]
+        O.lib().nmo_esat(C.c_float(t - 0.5), out); lo = out[0]
+        O.lib().nmo_esat(C.c_float(t), out)
+        assert out[2] == pytest.approx(hi - lo, rel=1.5e-2), t
+
+
+@pytest.mark.parametrize("smcmax,quartz", [(0.339, 0.92), (0.439, 0.40), (0.468, 0.25), (0.476, 0.10)])
+def test_tdfcnd_limits_of_the_johansen_conductivity(O, smcmax, quartz):
+    """TDFCND (Peters-Lidard et al. 1998 / Johansen 1975): the dry limit is (0.135 rho_d + 64.7) / (2700 - 0.947 rho_d),
+    the saturated unfrozen limit k_s^(1-n) k_w^n with k_s = 7.7^q 2.0^(1-q), the saturated frozen limit k_s^(1-n) k_ice^n,
+    and conductivity grows with wetness in between."""
+    L = O.lib()
+    L.nmo_tdfcnd.argtypes = [C.c_float] * 4
+    L.nmo_tdfcnd.restype = C.c_float
+    rho_d = (1.0 - smcmax) * 2700.0
+    dry = (0.135 * rho_d + 64.7) / (2700.0 - 0.947 * rho_d)
+    ks = 7.7 ** quartz * 2.0 ** (1.0 - quartz)
+    assert L.nmo_tdfcnd(0.02 * smcmax, 0.02 * smcmax, smcmax, quartz) == pytest.approx(dry, rel=1e-5)   # Ke = 0 below 10 %
+    assert L.nmo_tdfcnd(smcmax, smcmax, smcmax, quartz) == pytest.approx(ks ** (1 - smcmax) * 0.57 ** smcmax, rel=1e-5)
+    assert L.nmo_tdfcnd(smcmax, 1e-9, smcmax, quartz) == pytest.approx(ks ** (1 - smcmax) * 2.2 ** smcmax, rel=1e-4)
+    w = [L.nmo_tdfcnd(f * smcmax, f * smcmax, smcmax, quartz) for f in (0.15, 0.3, 0.5, 0.7, 0.9, 1.0)]
+    assert all(b > a for a, b in zip(w, w[1:])) and dry < w[0]
+    assert 0.1 < dry < 0.4 and 0.8 < w[-1] < 3.0   # W/m/K: the range soils have
+
+
 @pytest.mark.parametrize("ic", [0, 1])
 @pytest.mark.parametrize("vegtyp,cosz,vai,rho,tau,alb", [(2, 0.8, 3.0, 0.11, 0.07, 0.15), (14, 0.3, 1.2, 0.07, 0.05, 0.6),
                                                          (7, 0.55, 6.0, 0.45, 0.34, 0.25), (11, 0.05, 0.4, 0.10, 0.10, 0.9)])
