@@ -367,3 +367,21 @@ def test_math_mode_sensitivity_defines_tolerances(O, tables_usgs):
     assert np.quantile(d, 0.999) < 0.05          # branch flips are rare ...
     assert (a["isnowxy"] != b["isnowxy"]).mean() < 2e-3
     assert np.abs(a["smois"] - b["smois"]).max() < 5e-3
+
+
+def test_oracle_state_matches_committed_fixture(O, tables_usgs):
+    """tests/golden/oracle_state.json (made by tests/golden/gen_oracle_state.py): the portable-math oracle reproduces
+    the committed CRC-32 of every state array; a change of the oracle's arithmetic has to be deliberate."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("gen_oracle_state", os.path.join(here, "gen_oracle_state.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "oracle_state.json")))
+    got = mod.state_crcs()
+    assert got.keys() == want.keys()
+    for case in want:
+        bad = [n for n in want[case] if want[case][n] != got[case][n]]
+        assert not bad, (case, bad)
