@@ -9,6 +9,8 @@ Bars (BASELINE.json north_star):
     (abs tolerance, max fraction of columns allowed outside it) because single-ulp differences can flip the
     model's hard thresholds (snow-layer creation, Newton exit) in isolated columns.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -465,3 +467,23 @@ def test_tile_size_limit_is_reported(built, tables_usgs):
     with pytest.raises(noahmp_b200.NoahmpError) as e:
         noahmp_b200.NoahMP(tables_usgs, 8192, 4096)
     assert "2^25" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_gpu_state_matches_committed_fixture(built, tables_usgs):
+    """The PARITY build reproduces the committed CRC-32 of every state array (tests/golden/oracle_state.json) without the
+    oracle in the loop: the fixture pins kernels and oracle to the same bits from round to round."""
+    import json
+    import zlib
+    import noahmp_b200
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    want = json.load(open(os.path.join(here, "oracle_state.json")))
+    for name, ni, nj, steps in (("C1", 10, 10, 24), ("C4", 48, 32, 6)):
+        cfg = _cfg(name, ni, nj)
+        _, st, state = make_case(cfg, tables_usgs)
+        m = _model(tables_usgs, (ni, nj), noahmp_b200.MATH_PARITY)
+        assert run_gpu(m, cfg, st, state, steps) is None
+        m.close()
+        w = want[f"{name}_{ni}x{nj}_{steps}steps"]
+        bad = [n for n in w if zlib.crc32(np.ascontiguousarray(state[n]).tobytes()) != w[n]]
+        assert not bad, (name, bad)
