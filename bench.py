@@ -3,20 +3,29 @@
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (N>1: under torchrun)
     python bench.py --impl reference --gpus N --steps K ...    # the CPU arm: the C++ oracle on the host cores
+    python bench.py --config C5 ...                            # opt_run=5: + WTABLE_mmf_noahmp every step (NCCL halo)
 
 A "step" is one pass of the hot path (one `noahmplsm` call = one hourly model step) over the whole CONUS 1 km
 domain (4608x3840, dveg=2, 40 % of columns with a 3-layer snow pack: BASELINE.json configs[2], the configuration
 the metric is quoted on; it fits one B200).  With N GPUs the domain is tiled exactly as
 mpp/module_mpp_land.F90 does (strong scaling of the fixed domain, no communication on the step path).
 
+The forcing is a 24-HOUR DIURNAL CYCLE: model step s (1-based) reads hour (s-1) mod 24 of the cycle that starts at
+the configuration's start time (C3: 2017-01-15 00 UTC), so steps W+1 .. W+K of every arm — `value`, `e2e`, the
+forcing pipeline, `cpu_baseline` and `--impl reference` — see the same hours of the day; the sunlit fraction of the
+timed steps and of the whole day is printed next to each number (night columns skip ALBEDO/TWOSTREAM and STOMATA,
+phys/module_sf_noahmplsm.F90:2356, :5389, so the hour of day is part of the workload).
+
   value : column-steps/s with state AND forcing already resident in HBM (device-timed, CUDA events, max over ranks)
   e2e   : the same metric through the reference-facing C-ABI call noahmp_b200_noahmplsm() with HOST forcing
-          buffers (RESIDENT state mode): every step copies that hour's 12 forcing planes host->device and reads
+          buffers (RESIDENT state mode): every step copies that hour's forcing planes host->device and reads
           TSK/HFX/LH/GRDFLX back to the host arrays.
   roofline : HBM roofline of the dominant kernel (land_kernel): 824 algorithmic bytes per column-step
            / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  compute_roofline : algorithmic FP32 operations and transcendental calls per column-step counted by the op-counting
+          instantiation of the oracle (profiles/r02_opcount.json) / measured FFMA and MUFU issue rates.
   cpu_baseline : the C++ oracle ("port": the Fortran reference cannot be compiled in this image) on the host
-          cores, on a bounded sample of the same workload.
+          cores, on a bounded sample (every 9th row) of the same workload at the same hours.
 """
 import argparse
 import json
@@ -32,39 +41,43 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_COLUMN_STEP = 824  # 87 words read + 119 words written at the noahmplsm boundary
-# from the ncu --set full capture of the CONUS launch (profiles/r01_ncu_land_conus_v10_summary.txt): DRAM bytes moved and
-# warp-instructions executed per column by land_kernel<dynveg>
-NCU_DRAM_BYTES_PER_COLUMN = (7.381587e9 + 8.687775e9) / 17694720   # profiles/r01_ncu_land_conus_v10_summary.txt
-NCU_WARP_INSTR_PER_COLUMN = 4832070937 / 17694720
+ALG_BYTES_WTABLE = 188           # + per land column per WTABLE_mmf_noahmp call (config 5)
 N_SM, SCHED_PER_SM = 148, 4
 FORCING_ORDER = ["coszin", "t", "qv", "u", "v", "swdown", "glw", "p", "p", "rainbl", "vegfra", "dz8w"]
-
-
-PCIE_H2D_GBPS = 55.5  # PCIe 5 x16 of the B200 box, tools/pcie_probe.py
+RING_HOURS = 24
+PCIE_H2D_GBPS = 55.5  # PCIe 5 x16 of the B200 box, tools/pcie_probe.py (profiles/r01_pcie.json)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C3")
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--grid", type=int, nargs=2, default=None, help="override ni nj (testing only)")
-    ap.add_argument("--cpu-sample", type=int, nargs=3, default=[1536, 1280, 40], help="ni nj steps of the CPU sample")
+    ap.add_argument("--cpu-stride", type=int, default=9, help="the CPU arms run every n-th row of the domain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunks", type=int, default=0, help="row chunks of the e2e pipeline (0 = library default)")
     ap.add_argument("--math", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--full-day", action="store_true", help="after the timed region, time 24 more steps (one whole day)")
     return ap.parse_args()
 
 
-def load_peaks():
+def load_json(*path):
     try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        with open(os.path.join(ROOT, *path)) as f:
+            return json.load(f)
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return None
+
+
+def load_peaks():
+    d = load_json("MEASURED_PEAKS.json")
+    if d and "hbm_gbs" in d:
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -106,27 +119,56 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_sample(cfg, tables_dict, ni, nj, nsteps, threads):
-    """Time the C++ oracle (host libm, `threads` host threads) on an ni x nj window of the workload."""
+def get_config(args):
+    from noahmp_b200 import synthetic as S
+    cfg = S.named_config(args.config)
+    if args.grid:
+        cfg.ni, cfg.nj = args.grid
+    return cfg
+
+
+def ring_step(k):
+    """0-based step counter k -> model step whose forcing is read: hour k mod 24 of the first day."""
+    return 1 + (k % RING_HOURS)
+
+
+def cpu_arm(cfg, tables_dict, stride, warm, steps, threads):
+    """The C++ oracle (host libm, `threads` host threads) on every `stride`-th row of the domain: `warm` untimed steps,
+    then `steps` timed ones — the same step numbers, hence the same hours of the day, as the GPU arm."""
     from noahmp_b200 import _capi, synthetic as S
     from oracle import oracle as O
     O.build()
     ts = _capi.tables_from_dict(tables_dict)
     xp = S.backend()
-    x0, y0 = (cfg.ni - ni) // 2 + 1, (cfg.nj - nj) // 2 + 1
-    st = S.static_fields(xp, cfg, x0, x0 + ni - 1, y0, y0 + nj - 1)
+    stride = max(1, min(stride, cfg.nj))
+    st = S.static_fields(xp, cfg, jstride=stride)
     state = S.cold_start(cfg, st, S.forcing(xp, cfg, 1, st), tables_dict)
-    ncol = int((st["xland"] < 1.5).sum())
+    if cfg.opts["iopt_run"] == 5:
+        wt, wsc = S.groundwater_fields(cfg, st, state)
+        wsc.update(ide=st["xland"].shape[1], jde=st["xland"].shape[0])  # the sample is its own domain
+    land = st["xland"] < 1.5
+    ncol = int(land.sum())
     O.set_math_mode(0)
-    elapsed = 0.0
-    for step in range(1, nsteps + 1):
-        arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, step, st), state, step)
+    elapsed, sunlit = 0.0, []
+    for k in range(warm + steps):
+        frc = S.forcing(xp, cfg, ring_step(k), st)
+        arr, sc = S.args_from(cfg, st, frc, state, 1 + k)
         t0 = time.perf_counter()
         status, _ = O.noahmplsm(arr, sc, ts, nthreads=threads)
-        elapsed += time.perf_counter() - t0
+        if cfg.opts["iopt_run"] == 5:
+            # the row sample has no physical neighbours: the lateral-flow stencil runs on it as on any grid (same work)
+            O.wtable(wt, wsc, ts)
+        dt = time.perf_counter() - t0
         if status.code:
-            raise RuntimeError(f"oracle conservation check failed at step {step}: {status.code}")
-    return ncol * nsteps / elapsed, ncol, elapsed
+            raise RuntimeError(f"oracle conservation check failed at step {1 + k}: code {status.code}")
+        if k >= warm:
+            elapsed += dt
+            sunlit.append(float((frc["coszin"][land] > 0).mean()))
+    nj = st["xland"].shape[0]
+    sample = (f"every {stride}th row of {cfg.name} {cfg.ni}x{cfg.nj} = {cfg.ni}x{nj} cells ({ncol} columns), steps "
+              f"{warm + 1}..{warm + steps} of the 24 h cycle (sunlit fraction {np.mean(sunlit):.3f}), {elapsed:.1f} s, "
+              f"C++ oracle -O2 host libm")
+    return ncol * steps / elapsed, ncol, elapsed, float(np.mean(sunlit)), sample
 
 
 def run_reference(args):
@@ -135,41 +177,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from noahmp_b200 import synthetic as S, tables
-    cfg = S.named_config(args.config)
-    if args.grid:
-        cfg.ni, cfg.nj = args.grid
+    from noahmp_b200 import tables
+    cfg = get_config(args)
     td = tables.default_tables("USGS")
     threads = os.cpu_count() or 1
-    ni, nj, _ = args.cpu_sample
-    ni, nj = min(ni, cfg.ni), min(nj, cfg.nj)
-    total = args.steps + args.warmup
-    # each "step" = one hourly step of the ni x nj sample window
-    from noahmp_b200 import _capi
-    from oracle import oracle as O
-    O.build()
-    ts = _capi.tables_from_dict(td)
-    xp = S.backend()
-    x0, y0 = (cfg.ni - ni) // 2 + 1, (cfg.nj - nj) // 2 + 1
-    st = S.static_fields(xp, cfg, x0, x0 + ni - 1, y0, y0 + nj - 1)
-    state = S.cold_start(cfg, st, S.forcing(xp, cfg, 1, st), td)
-    ncol = int((st["xland"] < 1.5).sum())
-    O.set_math_mode(0)
-    elapsed = 0.0
-    for step in range(1, total + 1):
-        arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, step, st), state, step)
-        t0 = time.perf_counter()
-        O.noahmplsm(arr, sc, ts, nthreads=threads)
-        dt = time.perf_counter() - t0
-        if step > args.warmup:
-            elapsed += dt
-    v = ncol * args.steps / elapsed
-    sample = f"{ni}x{nj} window ({ncol} columns) of {cfg.name} {cfg.ni}x{cfg.nj}, {args.steps} hourly steps"
+    v, ncol, elapsed, sunlit, sample = cpu_arm(cfg, td, args.cpu_stride, args.warmup, args.steps, threads)
     print(json.dumps({
         "impl": "reference", "metric": "column-timesteps/sec", "value": v, "unit": "column-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg, args.gpus),
+        "config": workload_config(cfg, args.gpus), "sunlit_fraction": sunlit,
         "cpu_baseline": {"value": v, "unit": "column-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -178,12 +195,17 @@ def run_reference(args):
 
 def workload_config(cfg, n):
     title = {"C3": "CONUS 1 km", "C4": "global 0.05 deg land mask incl. glacier", "C2": "NLDAS 0.125 deg",
-             "C1": "HRLDAS 10x10"}.get(cfg.name, cfg.name)
-    return {"workload": f"{cfg.name}: {title} {cfg.ni}x{cfg.nj} hourly NoahMP step, dveg={cfg.opts['idveg']} "
-                        f"opt_run={cfg.opts['iopt_run']}, {int(cfg.snow_frac * 100)}% columns with 3-layer snow",
+             "C1": "HRLDAS 10x10", "C5": "CONUS 1 km, MMF groundwater (WTABLE_mmf_noahmp after every step)"}.get(cfg.name, cfg.name)
+    y, mo, d, h = cfg.start
+    return {"workload": f"{cfg.name}: {title} {cfg.ni}x{cfg.nj} hourly NoahMP step over a 24 h diurnal cycle of forcing "
+                        f"(from {y}-{mo:02d}-{d:02d} {h:02d} UTC), dveg={cfg.opts['idveg']} opt_run={cfg.opts['iopt_run']}, "
+                        f"{int(cfg.snow_frac * 100)}% columns with 3-layer snow",
             "grid": [cfg.ni, cfg.nj], "tiling": f"mpp_land_partition {n} rank(s)",
+            "forcing": "24 hourly forcing states resident in HBM (value) / in pinned host memory (e2e); timed step s reads "
+                       "hour (s-1) mod 24",
             "l2": "inputs larger than L2 (state+forcing per rank >> 126 MB); no flush needed",
-            "parallelism": f"domain tiles x{n}, no collective on the step path"}
+            "parallelism": f"domain tiles x{n}, " + ("KCELL/HEAD halo over NCCL inside noahmp_b200_wtable" if cfg.name == "C5"
+                                                      else "no collective on the step path")}
 
 
 def main():
@@ -203,14 +225,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: noahmp_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    noahmp_b200.bind_numa(local)  # this rank's threads (and the host buffers they first touch) next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = S.named_config(args.config)
-    if args.grid:
-        cfg.ni, cfg.nj = args.grid
+    cfg = get_config(args)
+    c5 = cfg.opts["iopt_run"] == 5
     td = tables.default_tables("USGS")
     xs, xe, ys, ye = noahmp_b200.tile(cfg.ni, cfg.nj, world, rank)
     ni, nj = xe - xs + 1, ye - ys + 1
+    bounds = dict(ims=xs, ime=xe, its=xs, ite=xe, jms=ys, jme=ye, jts=ys, jte=ye, ide=cfg.ni, jde=cfg.nj)
 
     # ---- initial state (cold start on the device) and upload: not timed ------------------------------------------------
     xp = S.backend()
@@ -218,33 +241,49 @@ def main():
     frc1 = S.forcing(xp, cfg, 1, st)
     math = noahmp_b200.MATH_PARITY if args.math == "parity" else noahmp_b200.MATH_FAST
     model = noahmp_b200.NoahMP(td, ni, nj, device=local, sync=noahmp_b200.SYNC_RESIDENT, math=math)
-    state = S.cold_start_device(model, cfg, st, frc1, xs, ys)  # NOAHMP_INIT through the library (row f1)
+    if c5:
+        state = S.cold_start(cfg, st, frc1, td)
+        wt, wsc = S.groundwater_fields(cfg, st, state)
+        wsc.update(bounds)
+        if world > 1:  # the library's own NCCL communicator for the KCELL/HEAD halo (and the budget all-reduce)
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                uid = torch.from_numpy(model.comm_unique_id().copy())
+            uid = uid.to(dev)
+            dist.broadcast(uid, 0)
+            model.comm_init(uid.cpu().numpy(), rank, world)
+    else:
+        state = S.cold_start_device(model, cfg, st, frc1, xs, ys)  # NOAHMP_INIT through the library (row f1)
     if args.chunks:
         model.set_chunks(args.chunks)
     arr, sc = S.args_from(cfg, st, frc1, state, 1)
-    sc.update(ims=xs, ime=xe, its=xs, ite=xe, jms=ys, jme=ye, jts=ys, jte=ye, ide=cfg.ni, jde=cfg.nj)
+    sc.update(bounds)
     model.upload(arr, sc)
     census = model.census()
     ncol = census["land"] + census["glacier"]
 
-    # ---- forcing hours resident in HBM (ring of R hours generated on the device) -------------------------
-    R = 4
+    # ---- the 24 forcing hours resident in HBM (generated on the device) -------------------------------------------
     xt = S.backend(dev)
     st_t = S.static_fields(xt, cfg, xs, xe, ys, ye)
-    ring, clocks_yr = [], []
-    for h in range(R):
+    land_t = st_t["xland"] < 1.5
+    ring, sun = [], []
+    dz8w_t = torch.full((nj, ni), 60.0, device=dev)
+    vegfra_t = st_t["vegfra"].contiguous()
+    for h in range(RING_HOURS):
         f = S.forcing(xt, cfg, 1 + h, st_t)
         planes = {k: f[k].contiguous() for k in set(FORCING_ORDER) - {"vegfra", "dz8w"}}
-        planes["vegfra"] = st_t["vegfra"].contiguous()
-        planes["dz8w"] = torch.full((nj, ni), 60.0, device=dev)
+        planes["vegfra"], planes["dz8w"] = vegfra_t, dz8w_t
         ring.append([planes[k] for k in FORCING_ORDER])
+        sun.append(float(((f["coszin"] > 0) & land_t).sum()))
     torch.cuda.synchronize()
     stream = torch.cuda.Stream(device=dev)  # the physics kernels are launched on this stream and timed on it
 
     def device_step(k):  # k = 0-based global step counter
-        yr, julian, _ = S.clock(cfg, 1 + k)
-        model.bind_forcing([t.data_ptr() for t in ring[k % R]])
+        yr, julian, _ = S.clock(cfg, ring_step(k))
+        model.bind_forcing([t.data_ptr() for t in ring[k % RING_HOURS]])
         model.step_device(1 + k, yr, float(julian), float(cfg.dt), stream.cuda_stream)
+        if c5:
+            model.wtable_device(wt, wsc, stream.cuda_stream)  # WTABLE_mmf_noahmp incl. the halo exchange, same stream
 
     def barrier():
         if world > 1:
@@ -263,7 +302,9 @@ def main():
     barrier()
     if rank == 0:
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    nsteps = args.steps + (RING_HOURS if args.full_day else 0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
+    k_first = k
     ev[0].record(stream)
     for s in range(args.steps):
         device_step(k); k += 1
@@ -271,50 +312,68 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     gpu_launches = model.launches - launches0
-    step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[-1])
+    for s in range(args.steps, nsteps):  # optional: one more whole day, outside the K timed steps
+        device_step(k); k += 1
+        ev[s + 1].record(stream)
+    torch.cuda.synchronize()
+    step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(nsteps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
     st1 = model.status()
     if st1.code:
         raise SystemExit(f"model conservation check failed: code {st1.code} at ({st1.i},{st1.j}) value {st1.value}")
     model.bind_forcing(None)
+    timed_hours = [(k_first + s) % RING_HOURS for s in range(args.steps)]
 
     # ---- end-to-end through the reference-facing call with host forcing ("e2e") ---------------------------
     e2e = None
-    if not args.no_e2e:
+    run_e2e = not args.no_e2e and not c5
+    if run_e2e:
+        cudart = torch.cuda.cudart()
+        names3d = {"t": "t3d", "qv": "qv3d", "u": "u_phy", "v": "v_phy", "p": "p8w3d"}
+        names2d = {"coszin": "coszin", "swdown": "swdown", "glw": "glw", "rainbl": "rainbl"}
+        idx = {n: i for i, n in enumerate(FORCING_ORDER)}
+
+        def pinned(shape):
+            a = np.empty(shape, np.float32)
+            cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            return a
+
         host_ring = []
-        for h in range(R):
+        for h in range(RING_HOURS):
             hf = {}
-            f = ring[h]
-            names = ["coszin", "t3d", "qv3d", "u_phy", "v_phy", "swdown", "glw", "p8w3d", None, "rainbl", "vegfra",
-                     "dz8w"]
-            for idx, n in enumerate(names):
-                if n is None:
-                    continue
-                if n in _capi.ATM3D:
-                    t = torch.empty((nj, 2, ni), dtype=torch.float32).pin_memory()
-                    t[:, 0, :] = f[idx].cpu(); t[:, 1, :] = f[idx].cpu()
-                else:
-                    t = f[idx].cpu().pin_memory()
-                hf[n] = t
+            for src, n in names3d.items():
+                a = pinned((nj, 2, ni))
+                lev = ring[h][idx[src]]
+                torch.from_numpy(a).copy_(torch.stack([lev, lev], dim=1))  # levels 1 and 2 identical (driver :338)
+                hf[n] = a
+            for src, n in names2d.items():
+                a = pinned((nj, ni))
+                torch.from_numpy(a).copy_(ring[h][idx[src]])
+                hf[n] = a
             host_ring.append(hf)
         out_names = ["tsk", "hfx", "lh", "grdflx"]
-        pinned_out = {n: torch.from_numpy(state[n]).pin_memory() for n in out_names}
         e_arr = dict(arr)
         for n in out_names:
-            e_arr[n] = pinned_out[n].numpy()
+            a = pinned(state[n].shape)
+            a[...] = state[n]
+            e_arr[n] = a
         model.set_fetch(out_names)
-        h2d = sum(4 * ni * nj for _ in range(12))
+        # DZ8W (= 2*zlvl) never changes, VEGFRA changes when a forcing file brings a new one (not in this workload), and
+        # the driver copies level 1 of P8W3D into level 2: declared, those three planes cross PCIe once, not every step
+        model.set_forcing_hints(noahmp_b200.HINT_DZ8W_CONSTANT | noahmp_b200.HINT_VEGFRA_UNCHANGED |
+                                noahmp_b200.HINT_P8W_LEVELS_EQUAL)
+        nup = 9
+        h2d = 4 * ni * nj * nup
         d2h = 4 * ni * nj * len(out_names)
+        prep = model.prepare(e_arr, sc)
 
         def e2e_step(k):
-            yr, julian, _ = S.clock(cfg, 1 + k)
-            a = dict(e_arr)
-            for n, t in host_ring[k % R].items():
-                a[n] = t.numpy()
-            s2 = dict(sc)
-            s2.update(itimestep=1 + k, yr=yr, julian=float(julian))
-            return model.noahmplsm(a, s2)  # forcing upload | physics | TSK/HFX/LH/GRDFLX download, pipelined by row chunks
+            yr, julian, _ = S.clock(cfg, ring_step(k))
+            # forcing upload | physics | TSK/HFX/LH/GRDFLX download, pipelined by row chunks
+            return model.noahmplsm_prepared(prep, 1 + k, yr, float(julian), host_ring[k % RING_HOURS])
 
+        # same hours of the day as the device-resident timing: resume at the next step whose hour is k_first's
+        k += (k_first - args.warmup - k) % RING_HOURS
         for _ in range(max(1, args.warmup)):
             e2e_step(k); k += 1
         barrier()
@@ -325,98 +384,138 @@ def main():
         e2e_s = time.perf_counter() - t0
         if stt.code:
             raise SystemExit(f"e2e: model check failed code {stt.code}")
-        e2e = (e2e_s, h2d, d2h)
+        e2e = (e2e_s, h2d, d2h, nup)
+        model.set_forcing_hints(0)
 
     # ---- e2e through the on-device forcing pipeline (row f2): forcing FILES every 3 h, interpolation on the GPU ------
     e2e_f2 = None
-    if not args.no_e2e:
-        idx = {n: i for i, n in enumerate(FORCING_ORDER)}
+    if run_e2e:
         files = []
-        for h in range(R):
+        for h in range(0, RING_HOURS, 3):
             f = ring[h]
             d = {"t": f[idx["t"]], "q": f[idx["qv"]], "u": f[idx["u"]], "v": f[idx["v"]], "p": f[7], "lw": f[idx["glw"]],
                  "sw": f[idx["swdown"]], "pcp": f[idx["rainbl"]] / float(cfg.dt), "fpar": f[idx["vegfra"]] / 100.0}
-            files.append({n: t.float().cpu().pin_memory().numpy() for n, t in d.items()})
+            hf = {}
+            for n, t in d.items():
+                a = pinned((nj, ni))
+                torch.from_numpy(a).copy_(t.float())
+                hf[n] = a
+            files.append(hf)
+        nf = len(files)
         model.forcing_static(st["xlatin"], st["xlong"], 30.0)
-        model.forcing_upload(0, files[0]); model.forcing_upload(1, files[1])
-        nfile = 1
+        k += (k_first - 3 - k) % RING_HOURS
+        fa = ((k % RING_HOURS) // 3) % nf
+        model.forcing_upload(0, files[fa]); model.forcing_upload(1, files[(fa + 1) % nf])
+        state_f2 = {"file": fa, "first": True}
 
-        def f2_step(k, count):
-            nonlocal nfile
-            sub = count % 3
-            if sub == 0 and count > 0:  # the model time reached file B
+        def f2_step(k):
+            hour = k % RING_HOURS
+            sub = hour % 3
+            if sub == 0 and not state_f2["first"]:  # the model time reached file B
                 model.forcing_swap()
-                nfile += 1
-                model.forcing_upload(1, files[nfile % R])  # asynchronous; overlaps the steps below
-            yr, julian, hour = S.clock(cfg, 1 + k)
-            jul = model.forcing_apply(float(np.float32(3 - sub) / np.float32(3)), int(julian), int(hour), 0, 0, float(cfg.dt))
-            s2 = dict(sc)
-            s2.update(itimestep=1 + k, yr=yr, julian=jul)
-            return model.noahmplsm_device_forcing(e_arr, s2)
+                state_f2["file"] = (state_f2["file"] + 1) % nf
+                model.forcing_upload(1, files[(state_f2["file"] + 1) % nf])  # asynchronous; overlaps the steps below
+            state_f2["first"] = False
+            yr, julian, hr = S.clock(cfg, ring_step(k))
+            jul = model.forcing_apply(float(np.float32(3 - sub) / np.float32(3)), int(julian), int(hr), 0, 0, float(cfg.dt))
+            return model.noahmplsm_prepared(prep, 1 + k, yr, jul, None, device_forcing=True)
 
-        cnt = 0
         for _ in range(3):
-            f2_step(k, cnt); k += 1; cnt += 1
+            f2_step(k); k += 1
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            stt = f2_step(k, cnt); k += 1; cnt += 1
+            stt = f2_step(k); k += 1
         barrier()
         e2e_f2 = time.perf_counter() - t0
         if stt.code:
             raise SystemExit(f"e2e (forcing pipeline): model check failed code {stt.code}")
 
     # ---- reduce over ranks ---------------------------------------------------------------------------------
-    vals = torch.tensor([total_ms, float(ncol), e2e[0] if e2e else 0.0, float(gpu_launches), e2e_f2 or 0.0], device=dev,
-                        dtype=torch.float64)
+    vals = torch.tensor([total_ms, float(ncol), e2e[0] if e2e else 0.0, float(gpu_launches), e2e_f2 or 0.0,
+                         float(census["land"])] + sun + step_ms, device=dev, dtype=torch.float64)
     if world > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         total_ms, e2e_s_max, e2e_f2 = float(mx[0]), float(mx[2]), float(mx[4])
-        ncol_all, launches_all = float(sm[1]), int(sm[3])
+        ncol_all, launches_all, nland_all = float(sm[1]), int(sm[3]), float(sm[5])
+        sun_all = [float(x) for x in sm[6:6 + RING_HOURS]]
+        step_ms_max = [float(x) for x in mx[6 + RING_HOURS:]]
     else:
-        e2e_s_max, ncol_all, launches_all = (e2e[0] if e2e else 0.0), float(ncol), int(gpu_launches)
-
+        e2e_s_max, ncol_all, launches_all, nland_all = (e2e[0] if e2e else 0.0), float(ncol), int(gpu_launches), float(census["land"])
+        sun_all, step_ms_max = sun, step_ms
     if rank == 0:
         peak, peak_src = load_peaks()
+        # sunlit fraction of the (non-water) cells, per hour of the cycle
+        sun_frac = [s / max(ncol_all, 1.0) for s in sun_all]
+        sun_timed = float(np.mean([sun_frac[h] for h in timed_hours]))
         value = ncol_all * args.steps / (total_ms * 1e-3)
-        # dominant kernel = land_kernel: the timed region is (memsets +) land kernel per step on this rank
-        mean_ms = float(np.mean(step_ms))
-        achieved = ALG_BYTES_PER_COLUMN_STEP * ncol / (mean_ms * 1e-3) / 1e9
-        try:  # measured FP32 issue peak of this GPU type (thread-instructions/s -> warp-instructions/s)
-            with open(os.path.join(ROOT, "profiles", "r01_peaks.json")) as f:
-                issue_peak, measured_issue = json.load(f)["ffma_thread_instr_per_s"] / 32.0, True
-        except Exception:
-            issue_peak, measured_issue = N_SM * SCHED_PER_SM * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6, False
+        # dominant kernel = land_kernel: the timed region is land kernel (+ re-binning every 20 steps, + glacier / sea-ice
+        # kernels when present) per step on this rank
+        mean_ms = float(np.mean(step_ms[:args.steps]))
+        alg_bytes = ALG_BYTES_PER_COLUMN_STEP + (ALG_BYTES_WTABLE if c5 else 0)
+        achieved = alg_bytes * ncol / (mean_ms * 1e-3) / 1e9
+        kc = load_json("profiles", "r02_kernel_constants.json") or {}
+        peaks = load_json("profiles", "r01_peaks.json") or {}
+        opc = load_json("profiles", "r02_opcount.json") or {}
         line = {
             "metric": "column-timesteps/sec", "value": value, "unit": "column-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, world),
+            "sunlit_fraction": sun_timed, "sunlit_fraction_24h": float(np.mean(sun_frac)),
+            "timed_hours_utc": [(cfg.start[3] + h) % 24 for h in timed_hours],
+            "step_ms": [round(x, 3) for x in step_ms_max[:args.steps]],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_COLUMN * ncol if cfg.name == "C3" else None,
-                         "traffic_source": "ncu dram__bytes_read+write of the CONUS launch, profiles/r01_ncu_land_conus_v10_summary.txt",
+                         "traffic": (kc.get("dram_bytes_per_column") * ncol) if kc.get("dram_bytes_per_column") and cfg.name == "C3" else None,
+                         "traffic_source": kc.get("source"),
                          "peak_source": peak_src, "kernel": f"land_kernel<{model.variant}>",
-                         "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLUMN_STEP,
+                         "algorithmic_bytes_per_column_step": alg_bytes,
                          "columns_per_launch": ncol, "kernel_ms": mean_ms,
-                         "note": "step = memset x2 + land_kernel (+glacier/sea-ice kernels when present); "
-                                 "the physics is FP32/SFU-issue bound, see DESIGN.md"},
-            # the binding resource: warp-instruction issue slots (FP32 / SFU pipes), not HBM
-            "issue_roofline": {"bound": "fp32/sfu issue", "warp_instr_per_column": NCU_WARP_INSTR_PER_COLUMN,
-                               "achieved_warp_instr_per_s": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3),
-                               "peak_warp_instr_per_s": issue_peak,
-                               "peak_source": "measured FFMA issue rate, tools/peaks.cu -> profiles/r01_peaks.json"
-                                              if measured_issue else "nominal 148 SM x 4 schedulers x SM clock",
-                               "frac": NCU_WARP_INSTR_PER_COLUMN * ncol / (mean_ms * 1e-3) / issue_peak,
-                               "simt_efficiency": 0.772,
-                               "source": "instruction count from ncu (profiles/), time and clock measured live"},
+                         "note": "step = land_kernel (+ re-binning passes every 20 steps; + glacier/sea-ice kernels when "
+                                 "present); the physics is FP32/SFU-issue and latency bound, see compute_roofline and DESIGN.md"},
             "clocks": clocks, "gpu_launches": launches_all, "census": census, "math": args.math,
         }
+        if args.full_day:
+            day = step_ms_max[args.steps:args.steps + RING_HOURS]
+            hours = [(k_first + args.steps + s) % RING_HOURS for s in range(RING_HOURS)]
+            line["full_day"] = {"ms_per_step": float(np.mean(day)), "value": ncol_all / (float(np.mean(day)) * 1e-3),
+                                "by_hour_utc": {str((cfg.start[3] + h) % 24): round(t, 3) for h, t in zip(hours, day)},
+                                "sunlit_by_hour_utc": {str((cfg.start[3] + h) % 24): round(sun_frac[h], 3) for h in hours},
+                                "note": "24 consecutive steps after the K timed ones, CUDA events, max over ranks"}
+        # the binding resource: FP32 / SFU issue. Numerator = ALGORITHMIC operations per column-step counted by the
+        # op-counting instantiation of the oracle on this workload (tools/opcount.py), not executed instructions.
+        if opc.get(cfg.name if cfg.name != "C5" else "C3") and peaks:
+            o = opc[cfg.name if cfg.name != "C5" else "C3"]
+            colrate = ncol / (mean_ms * 1e-3)
+            fp32 = o["fp32_instr_per_column_step"] * colrate
+            mufu = o["mufu_per_column_step"] * colrate
+            line["compute_roofline"] = {
+                "bound": "fp32/sfu issue",
+                "fp32_instr_per_column_step": o["fp32_instr_per_column_step"], "mufu_per_column_step": o["mufu_per_column_step"],
+                "fp32": {"achieved_thread_instr_per_s": fp32, "peak": peaks["ffma_thread_instr_per_s"],
+                         "frac": fp32 / peaks["ffma_thread_instr_per_s"]},
+                "mufu": {"achieved_thread_instr_per_s": mufu, "peak": peaks["mufu_ex2_thread_instr_per_s"],
+                         "frac": mufu / peaks["mufu_ex2_thread_instr_per_s"]},
+                "frac": fp32 / peaks["ffma_thread_instr_per_s"] + mufu / peaks["mufu_ex2_thread_instr_per_s"],
+                "source": "operation counts: profiles/r02_opcount.json (op-counting oracle, " + o.get("sample", "") +
+                          "); peaks: profiles/r01_peaks.json (tools/peaks.cu on this GPU type); frac = share of the SM's "
+                          "issue time the algorithmic FP32 and MUFU work needs at those rates"}
+        if kc.get("warp_instr_per_column"):
+            wi = kc["warp_instr_per_column"] * ncol / (mean_ms * 1e-3)
+            issue_peak = (peaks.get("ffma_thread_instr_per_s") or N_SM * SCHED_PER_SM * 32 * 1.965e9) / 32.0
+            line["issue_utilisation"] = {"executed_warp_instr_per_column": kc["warp_instr_per_column"],
+                                         "achieved_warp_instr_per_s": wi, "peak_warp_instr_per_s": issue_peak,
+                                         "frac": wi / issue_peak, "simt_efficiency": kc.get("simt_efficiency"),
+                                         "source": kc.get("source"),
+                                         "note": "executed instructions (a utilisation, not an algorithmic roofline)"}
         if e2e:
             line["e2e"] = {"value": ncol_all * args.steps / e2e_s_max, "unit": "column-steps/s",
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
-                           "call": "noahmp_b200_noahmplsm (RESIDENT state, set_fetch=tsk,hfx,lh,grdflx; 9 row chunks, half-height first and last), pinned host buffers",
-                           "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                           "call": "noahmp_b200_noahmplsm (RESIDENT state, set_fetch=tsk,hfx,lh,grdflx; row-chunk pipeline; "
+                                   f"{e2e[3]} forcing planes per call: DZ8W, VEGFRA and level 2 of P8W3D declared "
+                                   "constant / unchanged / equal to level 1 with noahmp_b200_set_forcing_hints), pinned host buffers",
+                           "ms_per_step": 1e3 * e2e_s_max / args.steps, "sunlit_fraction": sun_timed,
                            # the forcing upload is what bounds this call: bytes per rank / the box's pinned H2D rate
                            "pcie_floor_ms": e2e[1] / PCIE_H2D_GBPS / 1e6,
                            "pcie_note": f"{PCIE_H2D_GBPS} GB/s pinned H2D measured with tools/pcie_probe.py "
@@ -429,13 +528,10 @@ def main():
         else:
             line["e2e"] = None
         if world == 1 and not args.no_cpu_baseline:
-            sni, snj, sst = args.cpu_sample
-            sni, snj = min(sni, cfg.ni), min(snj, cfg.nj)
             threads = os.cpu_count() or 1
-            v, nc, el = cpu_oracle_sample(cfg, td, sni, snj, sst, threads)
+            v, nc, el, sl, sample = cpu_arm(cfg, td, args.cpu_stride, args.warmup, args.steps, threads)
             line["cpu_baseline"] = {"value": v, "unit": "column-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{sni}x{snj} window ({nc} columns) x {sst} steps of {cfg.name}, "
-                                              f"{el:.1f} s, C++ oracle -O2 host libm"}
+                                    "sample": sample, "sunlit_fraction": sl}
         print(json.dumps(line))
     model.close()
     if world > 1:

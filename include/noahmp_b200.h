@@ -205,9 +205,28 @@ int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* args);
  * The HRLDAS driver reads TSLB and LAI every step (module_hrldas_noahmp_driver.F90:567-572) and the output list
  * only every output_timestep (:440-565). */
 int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields);
+/* RESIDENT mode: INOUT fields whose HOST content every noahmp_b200_noahmplsm call takes again before the step (same
+ * syntax as set_fetch).  land_driver_exe overwrites LAI (passed as XLAIXY) from the forcing file before every call
+ * (driver/module_hrldas_noahmp_driver.F90:335, :403; driver/module_hrldas_netcdf_io.F90:1365, :1402): a resident
+ * drop-in lists "xlaixy" here. */
+int noahmp_b200_set_push(noahmp_b200_ctx* ctx, const char* fields);
+/* RESIDENT mode: forcing planes of the following calls that need no upload (a hint is a promise of the caller).
+ *   DZ8W_CONSTANT      DZ8W = 2*zlvl is set once by the driver (module_hrldas_noahmp_driver.F90:344)
+ *   VEGFRA_UNCHANGED   VEGFRA has not changed since the previous call (it changes when a forcing file is read,
+ *                      module_hrldas_netcdf_io.F90:1238-1246, :1401); clear the bit for the call after a change
+ *   P8W_LEVELS_EQUAL   levels kts and kts+1 of P8W3D hold the same values (the driver copies level 1 into level 2,
+ *                      module_hrldas_noahmp_driver.F90:338): level 2 is read from the level-1 plane
+ * A plane is sent at least once; withdrawing a hint makes the next call send it again. */
+#define NOAHMP_HINT_DZ8W_CONSTANT 1u
+#define NOAHMP_HINT_VEGFRA_UNCHANGED 2u
+#define NOAHMP_HINT_P8W_LEVELS_EQUAL 4u
+int noahmp_b200_set_forcing_hints(noahmp_b200_ctx* ctx, unsigned hints);
+/* Release the page-lock the library holds on one caller array (before the caller frees it). */
+int noahmp_b200_unpin(noahmp_b200_ctx* ctx, const void* host_array);
 /* RESIDENT mode runs as a pipeline over `nchunks` row chunks (forcing upload | physics | result download overlap);
- * 0 = automatic (1 for tiles below 2^20 cells, else 9 with the first and the last chunk half as tall as the others).
- * Must be set before the first re-binning. */
+ * 0 = automatic: one chunk below 2^20 cells, else about one per 2^21 cells, 3 to 9, the first and the last half as
+ * tall as the others from 4 chunks on.  After the first re-binning the chunking is fixed: other counts than the
+ * binned one and 1 fall back to it. */
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
 /* Divergence control (north_star item 4): in RESIDENT mode the land columns are physically re-ordered every
  * `interval` steps (default 20, 0 = never), inside their row chunk, into bins of equal snow-layer count and canopy
@@ -234,7 +253,8 @@ int noahmp_b200_bind_forcing(noahmp_b200_ctx* ctx, float* const* dev_ptrs /* [NO
  * scalars as in noahmplsm; `stream` is a cudaStream_t passed as void* (NULL = the context's stream). */
 int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt,
                             void* stream);
-/* Fetch status of the last step (synchronises the context stream). */
+/* Status since the previous get_status (or upload): the first failing column and the number of failing column-steps
+ * of all noahmp_b200_step_device calls in between (synchronises the device, then resets the latch). */
 int noahmp_b200_get_status(noahmp_b200_ctx* ctx, noahmp_status* status);
 /* Number of kernels launched by this context since creation (for bench accounting). */
 long long noahmp_b200_launch_count(const noahmp_b200_ctx* ctx);
@@ -311,6 +331,34 @@ int noahmp_b200_wtable_end(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args)
  * element (i - its + 1) + (j - jts + 1) * (ni + 2).  The caller exchanges the ring with the neighbouring tiles
  * (NCCL send/recv through its own communicator) between _begin and _end. */
 int noahmp_b200_wtable_halo(noahmp_b200_ctx* ctx, float** kcell, float** head);
+/* ---- multi-GPU exchanges of the path, over NCCL inside the library ----------------------------------------------
+ * One process per GPU, ranks laid out as mpp_land_partition does (rank = iprocx + iprocy*nprocx,
+ * mpp/module_mpp_land.F90:83-84, :124-141).  Rank 0 obtains the 128-byte NCCL id with comm_unique_id, the host
+ * program broadcasts it (MPI_Bcast in the Fortran driver, torch.distributed under torchrun), every rank calls
+ * comm_init.  From then on noahmp_b200_wtable exchanges the KCELL / HEAD halo with the up-to-8 neighbouring tiles
+ * itself (grouped ncclSend/ncclRecv: columns, then rows carrying the corners) and the tiles reproduce the sequential
+ * single-domain result; the reference's MPI build exchanges nothing and clips LATERALFLOW at tile edges
+ * (module_sf_noahmp_groundwater.F90:231-234, :254-257 with ids = its). */
+int noahmp_b200_comm_unique_id(void* id128);
+int noahmp_b200_comm_init(noahmp_b200_ctx* ctx, const void* id128, int rank, int nranks);
+/* ranks of the left, right, lower (smaller j) and upper neighbour tile, -1 at the domain edge */
+int noahmp_b200_comm_neighbours(const noahmp_b200_ctx* ctx, int neighbours[4]);
+/* The halo exchange alone, between _begin and _end, on `stream` (cudaStream_t as void*, NULL = the context's). */
+int noahmp_b200_wtable_exchange(noahmp_b200_ctx* ctx, void* stream);
+/* noahmp_b200_wtable for a device-side stepping loop (RESIDENT mode): pass 1, halo, pass 2 and the column update are
+ * enqueued on `stream` behind the preceding noahmp_b200_step_device; nothing is copied and the host does not wait. */
+int noahmp_b200_wtable_device(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args, void* stream);
+
+/* Global water / energy budget (north_star: NCCL "for global water/energy-balance diagnostics").  When enabled, a
+ * reduction kernel follows every step and keeps eight fp64 sums over the land + glacier columns of the tile:
+ *   [0] storage now: CANWAT + SNOW + WA + sum_k SMOIS_k*DZS_k*1000 (mm)   [1] precipitation RAINBL (mm, accumulated)
+ *   [2] (ECAN+EDIR+ETRAN)*DT (mm, accumulated)   [3] (RUNSF+RUNSB)*DT (mm, accumulated)
+ *   [4] SAV+SAG-(FIRA+HFX+LH+GRDFLX), the ERRENG residual of ERROR (noahmplsm.F90:1188-1199) (W/m2, accumulated)
+ *   [5] SNOW now (mm)   [6] columns   [7] steps accumulated
+ * budget_read copies them out; global != 0 first sums them over the communicator (one ncclAllReduce of 8 doubles).
+ * Over an interval, d[0] - ([1]-[2]-[3]) is the sum of the per-column ERRWAT (noahmplsm.F90:1204-1226). */
+int noahmp_b200_budget_enable(noahmp_b200_ctx* ctx, int enable);
+int noahmp_b200_budget_read(noahmp_b200_ctx* ctx, double* out8, int global, int reset);
 int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args* args);
 
 /* ---- output / restart staging --------------------------------------------------

@@ -104,6 +104,9 @@ def array_dtype(name):
     return np.int32 if name in INT_ARRAYS else np.float32
 
 
+ARG_POINTER_TYPE = {n: _K[k] for n, k in ARGS_SPEC if k in ("pf", "pi")}
+
+
 def make_args(arrays, scalars):
     """Build a NoahmpLsmArgs from dicts. `arrays` values must be C-contiguous numpy arrays with the
     shapes of array_shape(); the struct keeps no reference, so keep `arrays` alive during the call."""

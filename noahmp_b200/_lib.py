@@ -37,6 +37,9 @@ SYMBOLS = {
     "noahmp_b200_noahmplsm": (C.c_int, [_ctx, _pa, _ps]),
     "noahmp_b200_sync_host": (C.c_int, [_ctx, _pa]),
     "noahmp_b200_set_fetch": (C.c_int, [_ctx, C.c_char_p]),
+    "noahmp_b200_set_push": (C.c_int, [_ctx, C.c_char_p]),
+    "noahmp_b200_set_forcing_hints": (C.c_int, [_ctx, C.c_uint]),
+    "noahmp_b200_unpin": (C.c_int, [_ctx, C.c_void_p]),
     "noahmp_b200_set_rebin": (C.c_int, [_ctx, C.c_int]),
     "noahmp_b200_rebin_count": (C.c_int, [_ctx]),
     "noahmp_b200_set_chunks": (C.c_int, [_ctx, C.c_int]),
@@ -67,6 +70,13 @@ SYMBOLS = {
     "noahmp_b200_wtable_end": (C.c_int, [_ctx, _pw]),
     "noahmp_b200_wtable_halo": (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "noahmp_b200_wtable_sync_host": (C.c_int, [_ctx, _pw]),
+    "noahmp_b200_wtable_exchange": (C.c_int, [_ctx, C.c_void_p]),
+    "noahmp_b200_wtable_device": (C.c_int, [_ctx, _pw, C.c_void_p]),
+    "noahmp_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "noahmp_b200_comm_init": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int]),
+    "noahmp_b200_comm_neighbours": (C.c_int, [_ctx, C.POINTER(C.c_int)]),
+    "noahmp_b200_budget_enable": (C.c_int, [_ctx, C.c_int]),
+    "noahmp_b200_budget_read": (C.c_int, [_ctx, C.POINTER(C.c_double), C.c_int, C.c_int]),
     "noahmp_b200_proc_grid": (None, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "noahmp_b200_tile": (None, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
 }

@@ -20,20 +20,70 @@ NMP_DEV float top7(const L7& a, int isnow) {
 
 NMP_DEV float TDC(float T) { return MIN(50.f, MAX(-50.f, (T - TFRZ))); }
 
-// noahmplsm.F90:5272-5321 (identical in glacier.F90:1150-1199)
+// noahmplsm.F90:5272-5321 (identical in glacier.F90:1150-1199): four degree-6 polynomials in T (deg C) — saturation
+// vapour pressure over water / ice and their temperature derivatives.  Every caller keeps only the pair the sign of
+// T selects (`IF (T .GT. 0.) THEN ESTV = ESATW ... ELSE ESTV = ESATI`), so the two entry points below evaluate only
+// what is kept: the warp skips the water (ice) polynomials when no lane is above (below) freezing.  Each polynomial is
+// the reference's Horner form, so the selected values have the bits the four-output routine gives.
+namespace esat_c {
+constexpr float EA0 = 6.107799961f, EA1 = 4.436518521E-01f, EA2 = 1.428945805E-02f, EA3 = 2.650648471E-04f,
+                EA4 = 3.031240396E-06f, EA5 = 2.034080948E-08f, EA6 = 6.136820929E-11f;
+constexpr float EB0 = 6.109177956f, EB1 = 5.034698970E-01f, EB2 = 1.886013408E-02f, EB3 = 4.176223716E-04f,
+                EB4 = 5.824720280E-06f, EB5 = 4.838803174E-08f, EB6 = 1.838826904E-10f;
+constexpr float EC0 = 4.438099984E-01f, EC1 = 2.857002636E-02f, EC2 = 7.938054040E-04f, EC3 = 1.215215065E-05f,
+                EC4 = 1.036561403E-07f, EC5 = 3.532421810e-10f, EC6 = -7.090244804E-13f;
+constexpr float ED0 = 5.030305237E-01f, ED1 = 3.773255020E-02f, ED2 = 1.267995369E-03f, ED3 = 2.477563108E-05f,
+                ED4 = 3.005693132E-07f, ED5 = 2.158542548E-09f, ED6 = 7.131097725E-12f;
+}  // namespace esat_c
+NMP_DEV float ESAT_W(float T) {
+  using namespace esat_c;
+  return 100.f * (EA0 + T * (EA1 + T * (EA2 + T * (EA3 + T * (EA4 + T * (EA5 + T * EA6))))));
+}
+NMP_DEV float ESAT_I(float T) {
+  using namespace esat_c;
+  return 100.f * (EB0 + T * (EB1 + T * (EB2 + T * (EB3 + T * (EB4 + T * (EB5 + T * EB6))))));
+}
+NMP_DEV float DESAT_W(float T) {
+  using namespace esat_c;
+  return 100.f * (EC0 + T * (EC1 + T * (EC2 + T * (EC3 + T * (EC4 + T * (EC5 + T * EC6))))));
+}
+NMP_DEV float DESAT_I(float T) {
+  using namespace esat_c;
+  return 100.f * (ED0 + T * (ED1 + T * (ED2 + T * (ED3 + T * (ED4 + T * (ED5 + T * ED6))))));
+}
 NMP_DEV void ESAT(float T, float& ESW, float& ESI, float& DESW, float& DESI) {
-  const float A0 = 6.107799961f, A1 = 4.436518521E-01f, A2 = 1.428945805E-02f, A3 = 2.650648471E-04f,
-              A4 = 3.031240396E-06f, A5 = 2.034080948E-08f, A6 = 6.136820929E-11f;
-  const float B0 = 6.109177956f, B1 = 5.034698970E-01f, B2 = 1.886013408E-02f, B3 = 4.176223716E-04f,
-              B4 = 5.824720280E-06f, B5 = 4.838803174E-08f, B6 = 1.838826904E-10f;
-  const float C0 = 4.438099984E-01f, C1 = 2.857002636E-02f, C2 = 7.938054040E-04f, C3 = 1.215215065E-05f,
-              C4 = 1.036561403E-07f, C5 = 3.532421810e-10f, C6 = -7.090244804E-13f;
-  const float D0 = 5.030305237E-01f, D1 = 3.773255020E-02f, D2 = 1.267995369E-03f, D3 = 2.477563108E-05f,
-              D4 = 3.005693132E-07f, D5 = 2.158542548E-09f, D6 = 7.131097725E-12f;
-  ESW = 100.f * (A0 + T * (A1 + T * (A2 + T * (A3 + T * (A4 + T * (A5 + T * A6))))));
-  ESI = 100.f * (B0 + T * (B1 + T * (B2 + T * (B3 + T * (B4 + T * (B5 + T * B6))))));
-  DESW = 100.f * (C0 + T * (C1 + T * (C2 + T * (C3 + T * (C4 + T * (C5 + T * C6))))));
-  DESI = 100.f * (D0 + T * (D1 + T * (D2 + T * (D3 + T * (D4 + T * (D5 + T * D6))))));
+  ESW = ESAT_W(T); ESI = ESAT_I(T); DESW = DESAT_W(T); DESI = DESAT_I(T);
+}
+#ifndef NMP_ESAT_SEL
+#define NMP_ESAT_SEL 1
+#endif
+// ES = (T > 0) ? ESATW : ESATI and the matching derivative
+NMP_DEV void ESAT_SEL(float T, float& ES, float& DES) {
+#if NMP_ESAT_SEL
+  const bool w = T > 0.f;
+  const unsigned m = __activemask();
+  float ew = 0.f, dw = 0.f, ei = 0.f, di = 0.f;
+  if (__any_sync(m, w)) { ew = ESAT_W(T); dw = DESAT_W(T); }
+  if (__any_sync(m, !w)) { ei = ESAT_I(T); di = DESAT_I(T); }
+  ES = w ? ew : ei;
+  DES = w ? dw : di;
+#else
+  float a, b, c, d;
+  ESAT(T, a, b, c, d);
+  if (T > 0.f) { ES = a; DES = c; } else { ES = b; DES = d; }
+#endif
+}
+NMP_DEV float ESAT_SEL1(float T) {
+#if NMP_ESAT_SEL
+  const bool w = T > 0.f;
+  const unsigned m = __activemask();
+  float ew = 0.f, ei = 0.f;
+  if (__any_sync(m, w)) ew = ESAT_W(T);
+  if (__any_sync(m, !w)) ei = ESAT_I(T);
+  return w ? ew : ei;
+#else
+  return T > 0.f ? ESAT_W(T) : ESAT_I(T);
+#endif
 }
 
 // noahmplsm.F90:1957-2011
@@ -659,7 +709,7 @@ NMP_DEV void VEGE_FLUX(Ctx& c, const FluxIn& in, float VAI, float GAMMAV, float 
   int LITER = 0;
   float DTV = 0.f, HG = 0.f, H = 0.f;
   float FHG = 0.f, RAHG = 0.f, RAWG = 0.f, RB = 0.f;
-  float ESATW, ESATI, DSATW, DSATI, ESTV = 0.f, DESTV = 0.f, ESTG, DESTG = 0.f;
+  float ESTV = 0.f, DESTV = 0.f, ESTG, DESTG = 0.f;
   float CAH = 0.f, CVH = 0.f, CGH, COND, ATA, BTA, CSH, CAW, CEW, CTW, CGW, AEA, BEA, CEV, CTR, A, B;
   float RAHC = 1.f, RAWC;
   o.PSNSUN = 0.f; o.PSNSHA = 0.f;
@@ -669,8 +719,7 @@ NMP_DEV void VEGE_FLUX(Ctx& c, const FluxIn& in, float VAI, float GAMMAV, float 
   float LAISHAE = MIN(6.f, LAISHA / FVEG);
 
   float T = TDC(TG);
-  ESAT(T, ESATW, ESATI, DSATW, DSATI);
-  if (T > 0.f) ESTG = ESATW; else ESTG = ESATI;
+  ESTG = ESAT_SEL1(T);
 
   QSFC = 0.622f * EAIR / (in.PSFC - 0.378f * EAIR);
 
@@ -697,9 +746,7 @@ NMP_DEV void VEGE_FLUX(Ctx& c, const FluxIn& in, float VAI, float GAMMAV, float 
           RAWG, RB);
 
     T = TDC(TV);
-    ESAT(T, ESATW, ESATI, DSATW, DSATI);
-    if (T > 0.f) { ESTV = ESATW; DESTV = DSATW; }
-    else { ESTV = ESATI; DESTV = DSATI; }
+    ESAT_SEL(T, ESTV, DESTV);
 
     if (ITER == 1) {
       if (crs == 1) {
@@ -772,9 +819,7 @@ NMP_DEV void VEGE_FLUX(Ctx& c, const FluxIn& in, float VAI, float GAMMAV, float 
 #pragma unroll 1
   for (ITER = 1; ITER <= 5; ++ITER) {
     T = TDC(TG);
-    ESAT(T, ESATW, ESATI, DSATW, DSATI);
-    if (T > 0.f) { ESTG = ESATW; DESTG = DSATW; }
-    else { ESTG = ESATI; DESTG = DSATI; }
+    ESAT_SEL(T, ESTG, DESTG);
 
     o.IRG = CIR * POW4(TG) + AIR;
     o.SHG = CSH * (TG - TAH);
@@ -837,7 +882,7 @@ NMP_DEV void BARE_FLUX(Ctx& c, const FluxIn& in, float ZPD, float Z0M, float LAT
   SfcState s;
   s.MOZ = 0.f; s.FM = 0.f; s.FH = 0.f; s.FM2 = 0.f; s.FH2 = 0.f; s.FV = 0.1f; s.WSTAR = 0.f; s.MOZSGN = 0;
   float H = 0.f;
-  float ESATW, ESATI, DSATW, DSATI, ESTG = 0.f, DESTG;
+  float ESTG = 0.f, DESTG;
   float CSH = 0.f, CEV = 0.f, EHB = 0.f;
   const float Z0H = Z0M;
   float CIR = EMG * SB;
@@ -860,9 +905,7 @@ NMP_DEV void BARE_FLUX(Ctx& c, const FluxIn& in, float ZPD, float Z0M, float LAT
     EHB = 1.f / RAHB;
 
     float T = TDC(TGB);
-    ESAT(T, ESATW, ESATI, DSATW, DSATI);
-    if (T > 0.f) { ESTG = ESATW; DESTG = DSATW; }
-    else { ESTG = ESATI; DESTG = DSATI; }
+    ESAT_SEL(T, ESTG, DESTG);
 
     CSH = RHOAIR * CPAIR / RAHB;
     CEV = RHOAIR * CPAIR / GAMMA / (in.RSURF + RAWB);
@@ -886,8 +929,7 @@ NMP_DEV void BARE_FLUX(Ctx& c, const FluxIn& in, float ZPD, float Z0M, float LAT
     H = CSH * (TGB - SFCTMP);
 
     T = TDC(TGB);
-    ESAT(T, ESATW, ESATI, DSATW, DSATI);
-    if (T > 0.f) ESTG = ESATW; else ESTG = ESATI;
+    ESTG = ESAT_SEL1(T);
     QSFC = 0.622f * (ESTG * in.RHSUR) / (in.PSFC - 0.378f * (ESTG * in.RHSUR));
   }
 

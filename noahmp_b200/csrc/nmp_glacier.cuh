@@ -74,7 +74,7 @@ NMP_DEV void GLACIER_FLUX(Ctx& c, float EMG, float DF_TOP, float DZ_TOP, float S
   SfcState s;
   s.MOZ = 0.f; s.FM = 0.f; s.FH = 0.f; s.FM2 = 0.f; s.FH2 = 0.f; s.FV = 0.1f; s.WSTAR = 0.f; s.MOZSGN = 0;
   float H = 0.f;
-  float ESATW, ESATI, DSATW, DSATI, ESTG = 0.f, DESTG, CSH = 0.f, CEV = 0.f, RAHB = 1.f;
+  float ESTG = 0.f, DESTG, CSH = 0.f, CEV = 0.f, RAHB = 1.f;
   const float Z0H = Z0M;
   float CIR = EMG * SB;
   float CGH = 2.f * DF_TOP / DZ_TOP;
@@ -84,9 +84,7 @@ NMP_DEV void GLACIER_FLUX(Ctx& c, float EMG, float DF_TOP, float DZ_TOP, float S
     RAHB = MAX(1.f, 1.f / (CH * UR));
     float RAWB = RAHB;
     float T = TDC(TGB);
-    ESAT(T, ESATW, ESATI, DSATW, DSATI);
-    if (T > 0.f) { ESTG = ESATW; DESTG = DSATW; }
-    else { ESTG = ESATI; DESTG = DSATI; }
+    ESAT_SEL(T, ESTG, DESTG);
     CSH = RHOAIR * CPAIR / RAHB;
     CEV = RHOAIR * CPAIR / GAMMA / (RSURF + RAWB);
     IRB = CIR * POW4(TGB) - EMG * LWDN;
@@ -103,8 +101,7 @@ NMP_DEV void GLACIER_FLUX(Ctx& c, float EMG, float DF_TOP, float DZ_TOP, float S
     TGB = TGB + DTG;
     H = CSH * (TGB - SFCTMP);
     T = TDC(TGB);
-    ESAT(T, ESATW, ESATI, DSATW, DSATI);
-    if (T > 0.f) ESTG = ESATW; else ESTG = ESATI;
+    ESTG = ESAT_SEL1(T);
     QSFC = 0.622f * (ESTG * RHSUR) / (SFCPRS - 0.378f * (ESTG * RHSUR));
   }
   float SICEMAXV = SMC(1) - SH2O(1);
@@ -434,6 +431,7 @@ NMP_DEV void NOAHMP_GLACIER(Ctx& c, Col& g) {
                          g.FSR, g.FSA);
     const float EMG = 0.98f, RHSUR = 1.0f, RSURF = 1.0f;
     float GAMMA = CPAIR * g.SFCPRS / (0.622f * LATHEA);
+    NMP_PHASE_MAJOR();
     GLACIER_FLUX<O>(c, EMG, top7(DF, g.ISNOW), top7(DZSNSO, g.ISNOW), top7(g.STC, g.ISNOW), Z0MG, ZLVL, ZPD, QAIR,
                     g.SFCTMP, RHOAIR, g.SFCPRS, UR, GAMMA, RSURF, g.LWDN, RHSUR, g.SMC, EAIR, g.SAG, g.SNOWH, LATHEA,
                     g.SH2O, g.CM, g.CH, g.TG, g.QSFC, g.FIRA, g.FSH, g.FGEV, g.SSOIL, g.T2MB, g.Q2B, g.CHB2);
@@ -441,6 +439,7 @@ NMP_DEV void NOAHMP_GLACIER(Ctx& c, Col& g) {
     if (FIRE <= 0.f) c.fatal(NOAHMP_ERR_FIRE, FIRE);
     g.EMISSI = EMG;
     g.TRAD = POW((FIRE - (1.f - g.EMISSI) * g.LWDN) / (g.EMISSI * SB), 0.25f);
+    NMP_PHASE_MAJOR();
     TSNOSOI<O>(c, g.ISNOW, g.TBOT, g.ZSNSO, g.SSOIL, DF, HCPCT, ZBOT, g.DT, g.SNOWH, g.STC);
     if (NMP_OPT(stc) == 2) {
       if (g.SNOWH > 0.05f && g.TG > TFRZ) g.TG = TFRZ;
@@ -454,6 +453,7 @@ NMP_DEV void NOAHMP_GLACIER(Ctx& c, Col& g) {
   float QVAP = MAX(g.FGEV / LATHEA, 0.f);
   float QDEW = ABS(MIN(g.FGEV / LATHEA, 0.f));
   g.EDIR = QVAP - QDEW;
+  NMP_PHASE_MAJOR();
   // ---- WATER_GLACIER ----
   {
     float SNOFLOW = 0.f;

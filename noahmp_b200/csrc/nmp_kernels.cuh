@@ -195,6 +195,23 @@ __device__ __forceinline__ void store_column(const ColumnIO& io, const StepParam
   io.st(NMP_SLOT(smcwtdxy), o.SMCWTD);
 }
 
+// NMP_SMEM_TABLES: the parameter tables (noahmp_tables, 12.7 KB) staged per block in shared memory and indexed by
+// VEGTYP / SOILTYP from there (north_star item 2) instead of through L1 from global memory.
+#ifndef NMP_SMEM_TABLES
+#define NMP_SMEM_TABLES 0
+#endif
+#if NMP_SMEM_TABLES
+__device__ __forceinline__ const noahmp_tables* stage_tables(const StepParams& p) {
+  __shared__ noahmp_tables sT;
+  static_assert(sizeof(noahmp_tables) % 4 == 0, "tables are copied word by word");
+  const unsigned* src = reinterpret_cast<const unsigned*>(p.tables);
+  unsigned* dst = reinterpret_cast<unsigned*>(&sT);
+  for (unsigned k = threadIdx.x; k < sizeof(noahmp_tables) / 4; k += blockDim.x) dst[k] = __ldg(src + k);
+  __syncthreads();
+  return &sT;
+}
+#endif
+
 __device__ __forceinline__ void init_ctx(Ctx& c, const StepParams& p) {
   c.T = p.tables;
   c.o.dveg = p.opt[0]; c.o.crs = p.opt[1]; c.o.btr = p.opt[2]; c.o.run = p.opt[3]; c.o.sfc = p.opt[4];
@@ -216,6 +233,9 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   ColumnIO io(p, (long long)p.first + t, live);
   Ctx c;
   init_ctx(c, p);
+#if NMP_SMEM_TABLES
+  c.T = stage_tables(p);
+#endif
   Col s;
   load_common(io, p, s);
   s.ICE = 0;
@@ -278,13 +298,20 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
 }
 
 // ---- glacier columns: NOAHMP_GLACIER + sentinel fills (noahmpdrv.F90:552-628) ------------------------
+// Same launch shape as the land kernel (NMP_BLOCK threads, warps aligned to 128-byte plane segments, the block
+// walking NOAHMP_GLACIER in barrier-separated phases); padding threads and rejected columns redo a valid column
+// with the stores switched off so that every thread reaches the barriers.
 template <class O>
-__global__ void __launch_bounds__(128) glacier_kernel(const __grid_constant__ StepParams p) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.count) return;
-  const ColumnIO io(p, (long long)p.first + t, true);
+__global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) glacier_kernel(const __grid_constant__ StepParams p) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x - (p.first & 31);
+  bool live = t >= 0 && t < p.count;
+  if (!live) t = t < 0 ? 0 : p.count - 1;
+  ColumnIO io(p, (long long)p.first + t, live);
   Ctx c;
   init_ctx(c, p);
+#if NMP_SMEM_TABLES
+  c.T = stage_tables(p);
+#endif
   Col s;
   load_common(io, p, s);
   s.ICE = -1;
@@ -297,8 +324,10 @@ __global__ void __launch_bounds__(128) glacier_kernel(const __grid_constant__ St
     const int ivg = VEGTYP;
     if (ivg == p.isurban || ivg == 31 || ivg == 32 || ivg == 33) VEGTYP = p.isurban;
     if (REDPRM(c, VEGTYP, SOILTYP, 1, VEGTYP == p.isurban)) {
-      report_error(p, io.cell, c.err, c.errv);
-      return;
+      if (live) report_error(p, io.cell, c.err, c.errv);
+      c.err = 0;
+      io.on = false;
+      live = false;
     }
   }
   NOAHMP_GLACIER<O>(c, s);
@@ -319,8 +348,8 @@ __global__ void __launch_bounds__(128) glacier_kernel(const __grid_constant__ St
   o.RECH = 0.f; o.DEEPRECH = 0.f;
   o.SMCWTD = io.ld(NMP_SLOT(smcwtdxy));
   store_column(io, p, s, o);
-  if (p.vege_iters) p.vege_iters[io.cell] = 0;
-  if (c.err) report_error(p, io.cell, c.err, c.errv);
+  if (io.on && p.vege_iters) p.vege_iters[io.cell] = 0;
+  if (live && c.err) report_error(p, io.cell, c.err, c.errv);
 }
 
 template <class O>
@@ -337,7 +366,7 @@ void launch_pair(const StepParams& base, const nmpf::StepRange& r, cudaStream_t 
     StepParams p = base;
     p.first = r.glac_first;
     p.count = nglac;
-    glacier_kernel<O><<<(nglac + 127) / 128, 128, 0, stream>>>(p);
+    glacier_kernel<O><<<(nglac + (r.glac_first & 31) + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
     ++*launches;
   }
 }

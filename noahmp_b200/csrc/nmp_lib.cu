@@ -67,8 +67,14 @@ struct PlaneDesc {
   int layer, layers;
 };
 
+#include "nmp_comm.cuh"
+
 struct noahmp_b200_ctx {
   int device = 0, ni = 0, nj = 0;
+  NmpComm comm;                            // NCCL communicator of the tiles of one domain (optional)
+  double* d_budget = nullptr;              // NBUDGET running sums (noahmp_b200_budget_*)
+  bool budget_on = false;
+  int budget_steps = 0;
   long long ncell = 0;
   cudaStream_t stream = nullptr;
   noahmp_tables* d_tables = nullptr;
@@ -99,17 +105,27 @@ struct noahmp_b200_ctx {
   long long launches = 0;
   std::string variant;
   std::unordered_map<const void*, size_t> registered;
+  std::unordered_map<const void*, unsigned long long> reg_used;  // last use (pin_clock) of a registration
+  unsigned long long pin_clock = 0;
+  size_t pinned_bytes = 0, pin_budget = (size_t)64 << 30;         // LRU bound of the page-locked bytes
   // chunk pipeline of the RESIDENT-mode call
   std::vector<int> h_cell;                 // host copy of the column map (grid order, as classified)
   // column re-binning (divergence control): land columns are physically re-ordered inside each row chunk by
   // (canopy tile computed in the previous step yes/no, snow-layer count)
   int rebin_interval = 20, steps_since_rebin = 0, rebins = 0, bin_chunks = 0;
   bool binned = false;
-  float* d_state2 = nullptr;
+  float* d_state2 = nullptr;               // PERMUTE_GROUP scratch planes of the re-binning
+  std::vector<int> moved_planes;           // planes the re-binning permutes (INOUT + internal)
+  cudaEvent_t ev_rebin = nullptr;
   unsigned char* d_plane_kind = nullptr;
   int *d_cell2 = nullptr, *d_keys = nullptr, *d_keys2 = nullptr, *d_perm = nullptr, *d_iota = nullptr, *d_chunk = nullptr;
   std::vector<int> ch_land, ch_glac, ch_sea;  // compact range boundaries of the row chunks (size nchunks+1)
   std::vector<int> fetch;                  // fields refreshed on the host by every noahmplsm call
+  std::vector<int> push;                   // INOUT fields re-read from the host by every RESIDENT-mode call
+  PlaneDesc* d_fetch_planes = nullptr;     // plane descriptors of the fetch list (one scatter launch per range)
+  int n_fetch_planes = 0;
+  unsigned hints = 0;                      // NOAHMP_HINT_* (forcing planes that need no upload this call)
+  bool forc_valid[NFORC] = {};             // plane holds an upload of the caller's array
   int nchunks = 0;                         // 0 = automatic
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_k, ev_out, ev_plane;
@@ -227,25 +243,54 @@ __global__ void seaice_kernel(float* state, const int* __restrict__ cell, const 
 }
 
 // ---- helpers ------------------------------------------------------------------------------------------
+static void unpin_one(noahmp_b200_ctx* ctx, const void* p) {
+  auto it = ctx->registered.find(p);
+  if (it == ctx->registered.end()) return;
+  if (it->second) {
+    if (cudaHostUnregister(const_cast<void*>(p)) != cudaSuccess) cudaGetLastError();
+    ctx->pinned_bytes -= std::min(ctx->pinned_bytes, it->second);
+  }
+  ctx->registered.erase(it);
+  ctx->reg_used.erase(p);
+}
 static void pin(noahmp_b200_ctx* ctx, const void* p, size_t bytes) {
   // Only large arrays are page-locked: they come from mmap'ed allocations of their own, whereas small heap
   // arrays can share a page with other data, and a partially registered range makes cudaMemcpyAsync fail.
   if (!ctx->pin_host || !p || bytes < (size_t)(4u << 20)) return;
   auto it = ctx->registered.find(p);
-  if (it != ctx->registered.end() && it->second >= bytes) return;
-  if (it != ctx->registered.end()) cudaHostUnregister(const_cast<void*>(p));
+  if (it != ctx->registered.end() && (it->second >= bytes || it->second == 0)) {
+    ctx->reg_used[p] = ctx->pin_clock;
+    return;
+  }
+  if (it != ctx->registered.end()) unpin_one(ctx, p);
+  // A driver that hands fresh arrays to every call (a Python loop allocating its forcing per step) must not grow the
+  // page-locked set without bound: registrations not used by the current or the previous call are dropped, oldest
+  // first, once the budget (NOAHMP_B200_PIN_BUDGET_GB, default 64) would be exceeded.
+  if (ctx->pinned_bytes + bytes > ctx->pin_budget) {
+    std::vector<std::pair<unsigned long long, const void*>> old;
+    for (auto& kv : ctx->reg_used)
+      if (kv.second + 1 < ctx->pin_clock) old.push_back({kv.second, kv.first});
+    std::sort(old.begin(), old.end());
+    if (!old.empty()) cudaDeviceSynchronize();  // no copy may still be reading what is about to be unlocked
+    for (auto& e : old) {
+      if (ctx->pinned_bytes + bytes <= ctx->pin_budget) break;
+      unpin_one(ctx, e.second);
+    }
+  }
   cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
-  if (e == cudaSuccess) ctx->registered[p] = bytes;
+  if (e == cudaSuccess) { ctx->registered[p] = bytes; ctx->pinned_bytes += bytes; }
   else {
     cudaGetLastError();         // already pinned by the caller, or not pinnable: plain pageable copy
     ctx->registered[p] = 0;     // remember not to retry every call
-    if (e == cudaErrorHostMemoryAlreadyRegistered) ctx->registered[p] = bytes;
   }
+  ctx->reg_used[p] = ctx->pin_clock;
 }
 static void unpin_all(noahmp_b200_ctx* ctx) {
   for (auto& kv : ctx->registered)
     if (kv.second) { if (cudaHostUnregister(const_cast<void*>(kv.first)) != cudaSuccess) cudaGetLastError(); }
   ctx->registered.clear();
+  ctx->reg_used.clear();
+  ctx->pinned_bytes = 0;
 }
 
 static int check_bounds(const noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
@@ -409,7 +454,12 @@ static int classify(noahmp_b200_ctx* ctx) {
   ctx->nclass[CL_WATER] = (int)(nc - offset);
   if (ctx->np > ctx->np_alloc) {
     if (ctx->d_state) CK(cudaFree(ctx->d_state));
-    if (ctx->d_state2) { CK(cudaFree(ctx->d_state2)); ctx->d_state2 = nullptr; }
+    if (ctx->d_state2) {
+      CK(cudaFree(ctx->d_state2)); ctx->d_state2 = nullptr;
+      for (int** q : {&ctx->d_cell2, &ctx->d_keys, &ctx->d_keys2, &ctx->d_perm, &ctx->d_iota, &ctx->d_chunk}) {
+        CK(cudaFree(*q)); *q = nullptr;
+      }
+    }
     CK(cudaMalloc(&ctx->d_state, sizeof(float) * (size_t)NPLANES_ALLOC * (size_t)ctx->np));
     CK(cudaMemsetAsync(ctx->d_state + (size_t)PLANE_PREV_ITERS * (size_t)ctx->np, 0, sizeof(float) * (size_t)ctx->np,
                        ctx->stream));
@@ -494,8 +544,11 @@ static void decode_status(noahmp_b200_ctx* ctx, noahmp_status* st) {
 // ---- C ABI ----------------------------------------------------------------------------------------------
 extern "C" {
 
-static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks);
-static int rebin(noahmp_b200_ctx* ctx);
+struct ChunkRanges;
+static int budget_accumulate(noahmp_b200_ctx* ctx, float dt, cudaStream_t s);
+static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks, ChunkRanges* out);
+static int auto_chunks(const noahmp_b200_ctx* ctx);
+static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s);
 
 const char* noahmp_b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -525,6 +578,8 @@ noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int
   if (env && (!strcmp(env, "parity") || !strcmp(env, "1"))) ctx->math_mode = 1;
   env = getenv("NOAHMP_B200_PIN");
   if (env && !strcmp(env, "0")) ctx->pin_host = false;
+  env = getenv("NOAHMP_B200_PIN_BUDGET_GB");
+  if (env && atof(env) > 0.) ctx->pin_budget = (size_t)(atof(env) * 1073741824.0);
   bool ok = true;
   auto A = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false; };
   ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -568,7 +623,9 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   for (auto p : ctx->d_grid) cudaFree(p);
   cudaFree(ctx->d_state); cudaFree(ctx->d_planes); cudaFree(ctx->d_cell); cudaFree(ctx->d_class);
   cudaFree(ctx->d_cub); cudaFree(ctx->d_nsel); cudaFree(ctx->d_errkey); cudaFree(ctx->d_errcount);
-  cudaFree(ctx->d_vege_iters);
+  cudaFree(ctx->d_vege_iters); cudaFree(ctx->d_fetch_planes);
+  cudaFree(ctx->d_budget); cudaFree(ctx->comm.d_send); cudaFree(ctx->comm.d_recv); cudaFree(ctx->comm.d_budget_sum);
+  if (ctx->comm.comm && nccl_api()) nccl_api()->CommDestroy(ctx->comm.comm);
   cudaFree(ctx->d_state2); cudaFree(ctx->d_cell2); cudaFree(ctx->d_keys); cudaFree(ctx->d_keys2);
   cudaFree(ctx->d_perm); cudaFree(ctx->d_iota); cudaFree(ctx->d_chunk); cudaFree(ctx->d_plane_kind);
   for (auto& b : ctx->d_fb) for (auto p : b) cudaFree(p);
@@ -586,6 +643,7 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   if (ctx->d_outstage) cudaFree(ctx->d_outstage);
   for (auto e : ctx->ev_plane) if (e) cudaEventDestroy(e);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_rebin) cudaEventDestroy(ctx->ev_rebin);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -618,13 +676,18 @@ int noahmp_b200_upload(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
   if ((rc = upload_static(ctx, a))) return rc;
   if ((rc = upload_forcing(ctx, a))) return rc;
   if ((rc = classify(ctx))) return rc;
-  if ((rc = upload_state(ctx, a, /*all=*/!ctx->uploaded))) return rc;
+  // OUT arrays travel up as well when the tile has open-water cells: those cells have no column, and what comes
+  // back for them must be what the caller holds now, not what it held at the first call
+  if ((rc = upload_state(ctx, a, /*all=*/!ctx->uploaded || ctx->nclass[CL_WATER] > 0))) return rc;
   if ((rc = gather_fields(ctx))) return rc;
   ctx->base.state = ctx->d_state;
   ctx->base.cell = ctx->d_cell;
   ctx->base.np = ctx->np;
   ctx->base.np4 = (unsigned)(ctx->np * 4);
   ctx->uploaded = true;
+  for (int f = 0; f < NFORC; ++f) { ctx->forc_valid[f] = true; ctx->base.forc[f] = ctx->d_forc[f]; }
+  CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -652,31 +715,37 @@ int noahmp_b200_get_iteration_counts(noahmp_b200_ctx* ctx, int32_t* out) {
   return 0;
 }
 
-int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt, void* stream) {
+// `clear_latch`: the per-call entry points report the status of their own step; a device-side loop of step_device
+// calls keeps the first failure (smallest key) and the total count until noahmp_b200_get_status reads them.
+static int step_device_impl(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt, void* stream,
+                            bool clear_latch) {
   if (!ctx || !ctx->uploaded) { set_error("step_device before upload"); return NOAHMP_ERR_ARG; }
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-  ctx->last_step_stream = s;
   // a snapshot taken by output_begin on the library's stream must be complete before a caller stream changes the state
   if (ctx->out_pending && s != ctx->stream) CK(cudaStreamWaitEvent(s, ctx->ev_outready, 0));
+  if (ctx->last_step_stream && ctx->last_step_stream != s) {  // the stream changed between steps: keep them ordered
+    if (!ctx->ev_rebin) CK(cudaEventCreateWithFlags(&ctx->ev_rebin, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ev_rebin, ctx->last_step_stream));
+    CK(cudaStreamWaitEvent(s, ctx->ev_rebin, 0));
+  }
   if (ctx->sync_mode == NOAHMP_SYNC_RESIDENT && ctx->rebin_interval > 0 && ctx->nclass[CL_LAND] > 0) {
     if (itimestep > 1 && (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
-      int nch = ctx->bin_chunks ? ctx->bin_chunks
-                                : (ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 9 : 1));
-      if (nch > ctx->nj) nch = ctx->nj;
-      int rc = chunk_ranges(ctx, nch);
+      int rc = chunk_ranges(ctx, ctx->binned ? ctx->bin_chunks : auto_chunks(ctx), nullptr);
       if (rc) return rc;
-      CK(cudaDeviceSynchronize());  // earlier steps may be in flight on a caller stream
-      if ((rc = rebin(ctx))) return rc;
+      if ((rc = rebin(ctx, s))) return rc;
     }
     ctx->steps_since_rebin++;
   }
+  ctx->last_step_stream = s;
   StepParams p = ctx->base;
   p.itimestep = itimestep;
   p.yearlen = year_length(yr);
   p.julian = julian;
   p.dt = dt;
-  CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), s));
-  CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), s));
+  if (clear_latch) {
+    CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), s));
+  }
   if (itimestep == 1 && ctx->nclass[CL_WATER] > 0) {
     const int T = 256;
     first_step_water_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, s>>>(
@@ -695,7 +764,12 @@ int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float j
     ctx->launches++;
   }
   CK(cudaGetLastError());
+  if (ctx->budget_on) return budget_accumulate(ctx, dt, s);
   return 0;
+}
+
+int noahmp_b200_step_device(noahmp_b200_ctx* ctx, int itimestep, int yr, float julian, float dt, void* stream) {
+  return step_device_impl(ctx, itimestep, yr, julian, dt, stream, /*clear_latch=*/false);
 }
 
 int noahmp_b200_get_status(noahmp_b200_ctx* ctx, noahmp_status* status) {
@@ -705,11 +779,15 @@ int noahmp_b200_get_status(noahmp_b200_ctx* ctx, noahmp_status* status) {
   CK(cudaMemcpy(ctx->h_errkey, ctx->d_errkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(ctx->h_errcount, ctx->d_errcount, sizeof(int), cudaMemcpyDeviceToHost));
   decode_status(ctx, status);
+  // the latch has been read: start a new accumulation period for the device-side steps that follow
+  CK(cudaMemset(ctx->d_errkey, 0xff, sizeof(unsigned long long)));
+  CK(cudaMemset(ctx->d_errcount, 0, sizeof(int)));
   return status ? status->code : 0;
 }
 
 int noahmp_b200_sync_host(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
   if (!ctx || !a || !ctx->uploaded) return NOAHMP_ERR_ARG;
+  ++ctx->pin_clock;
   CK(cudaSetDevice(ctx->device));
   int rc = check_bounds(ctx, a);
   if (rc) return rc;
@@ -732,21 +810,50 @@ static int chunk_row(const noahmp_b200_ctx* ctx, int c, int nchunks) {
   const int u = c <= 0 ? 0 : (c >= nchunks ? units : 2 * c - 1);
   return (int)((long long)ctx->nj * u / units);
 }
-static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks) {
-  if (ctx->bin_chunks == nchunks && (int)ctx->ch_land.size() == nchunks + 1) return 0;
-  if (ctx->binned) { set_error("the number of row chunks cannot change after the columns were re-binned"); return NOAHMP_ERR_ARG; }
+// Automatic number of row chunks of the RESIDENT-mode pipeline: about one chunk per 2^21 cells, at least 3 and at
+// most 9 for tiles of 2^20 cells and more (17.7 M cells -> 9, 8.8 M -> 5, 2.2 M -> 3), one below that.  Every
+// chunk costs ~25 API calls on the host; a small tile in many chunks is bound by those, not by PCIe or the kernel.
+static int auto_chunks(const noahmp_b200_ctx* ctx) {
+  if (ctx->nchunks) return std::min(ctx->nchunks, ctx->nj);
+  if (ctx->ncell < (1LL << 20)) return 1;
+  const int n = 1 + (int)(ctx->ncell >> 21);
+  return std::min(std::min(9, std::max(3, n)), ctx->nj);
+}
+struct ChunkRanges {
+  int n = 0;
+  std::vector<int> row, land, glac, sea;  // size n + 1
+};
+// Compact ranges of `nchunks` row chunks.  Once the land columns have been re-binned they stay inside the row chunk
+// they were binned in, so only that chunking (ctx->bin_chunks) or a single chunk are valid afterwards: any other
+// request falls back to the binned chunking.
+static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks, ChunkRanges* out) {
   const int nland = ctx->nclass[CL_LAND], nglac = ctx->nclass[CL_GLACIER], nsea = ctx->nclass[CL_SEAICE];
-  const int* cl = ctx->h_cell.data();
-  auto lower = [&](int lo, int hi, int cell) { return (int)(std::lower_bound(cl + lo, cl + hi, cell) - cl); };
-  ctx->ch_land.assign(nchunks + 1, 0); ctx->ch_glac.assign(nchunks + 1, 0); ctx->ch_sea.assign(nchunks + 1, 0);
-  for (int c = 0; c <= nchunks; ++c) {
-    const int j = chunk_row(ctx, c, nchunks);
-    const int cell = j * ctx->ni;
-    ctx->ch_land[c] = c == nchunks ? nland : lower(0, nland, cell);
-    ctx->ch_glac[c] = c == nchunks ? nland + nglac : lower(nland, nland + nglac, cell);
-    ctx->ch_sea[c] = c == nchunks ? nland + nglac + nsea : lower(nland + nglac, nland + nglac + nsea, cell);
+  if (ctx->binned && nchunks != ctx->bin_chunks && nchunks != 1) nchunks = ctx->bin_chunks;
+  const bool stored = ctx->bin_chunks == nchunks && (int)ctx->ch_land.size() == nchunks + 1;
+  if (!stored && !(ctx->binned && nchunks == 1)) {
+    const int* cl = ctx->h_cell.data();
+    auto lower = [&](int lo, int hi, int cell) { return (int)(std::lower_bound(cl + lo, cl + hi, cell) - cl); };
+    ctx->ch_land.assign(nchunks + 1, 0); ctx->ch_glac.assign(nchunks + 1, 0); ctx->ch_sea.assign(nchunks + 1, 0);
+    for (int c = 0; c <= nchunks; ++c) {
+      const int j = chunk_row(ctx, c, nchunks);
+      const int cell = j * ctx->ni;
+      ctx->ch_land[c] = c == nchunks ? nland : lower(0, nland, cell);
+      ctx->ch_glac[c] = c == nchunks ? nland + nglac : lower(nland, nland + nglac, cell);
+      ctx->ch_sea[c] = c == nchunks ? nland + nglac + nsea : lower(nland + nglac, nland + nglac + nsea, cell);
+    }
+    ctx->bin_chunks = nchunks;
   }
-  ctx->bin_chunks = nchunks;
+  if (out) {
+    out->n = nchunks;
+    if (ctx->binned && nchunks == 1 && ctx->bin_chunks != 1) {
+      out->row = {0, ctx->nj};
+      out->land = {0, nland}; out->glac = {nland, nland + nglac}; out->sea = {nland + nglac, nland + nglac + nsea};
+    } else {
+      out->row.resize(nchunks + 1);
+      for (int c = 0; c <= nchunks; ++c) out->row[c] = chunk_row(ctx, c, nchunks);
+      out->land = ctx->ch_land; out->glac = ctx->ch_glac; out->sea = ctx->ch_sea;
+    }
+  }
   return 0;
 }
 
@@ -764,30 +871,34 @@ __global__ void bin_key_kernel(const float* __restrict__ state, long long np, in
   keys[n] = c * 32 + pb * 4 + min(max(-isnow, 0), 3);
   iota[n] = n;
 }
-// new[plane][i] = old[plane][perm[i]] for land columns, plain copy for the other classes; blockIdx.y = plane
-// OUT planes (plane_kind 1) are rewritten for every land column by the step that follows, so only their non-land
-// tail is carried over.
-// One thread moves its column in PERMUTE_GROUP planes: the permutation index is read once per group and the group's
-// gathers are in flight together.
+// scratch[g][i] = state[planes[g]][perm[i]] for the land columns i < nland of one group of planes.  One thread moves
+// its column in PERMUTE_GROUP planes: the permutation index is read once per group and the group's gathers are in
+// flight together.  The permuted group is then copied back over the planes it came from (a dense device-to-device
+// copy), so the re-binning needs PERMUTE_GROUP scratch planes instead of a second copy of the whole state.
+// OUT planes are rewritten for every land column by the step that follows and are not moved; the glacier / sea-ice
+// tail of every plane stays where it is.
 constexpr int PERMUTE_GROUP = 8;
-__global__ void permute_state_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ perm,
-                                     const unsigned char* __restrict__ plane_kind, long long np, int nland, int nplanes) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= np) return;
-  const bool land = i < nland;
-  const long long j = land ? (long long)perm[i] : i;
-  const int p0 = blockIdx.y * PERMUTE_GROUP;
+struct PermuteGroup { int plane[PERMUTE_GROUP]; int n; };
+__global__ void permute_state_kernel(const float* __restrict__ state, float* __restrict__ scratch,
+                                     const int* __restrict__ perm, PermuteGroup grp, long long np, int nland) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nland) return;
+  const long long j = (long long)perm[i];
   float v[PERMUTE_GROUP];
-  bool move[PERMUTE_GROUP];
-#pragma unroll
-  for (int g = 0; g < PERMUTE_GROUP; ++g) {
-    const int pl = p0 + g;
-    move[g] = pl < nplanes && (!land || plane_kind[pl] == 0);
-    if (move[g]) v[g] = src[(long long)pl * np + j];
-  }
 #pragma unroll
   for (int g = 0; g < PERMUTE_GROUP; ++g)
-    if (move[g]) dst[(long long)(p0 + g) * np + i] = v[g];
+    if (g < grp.n) v[g] = state[(long long)grp.plane[g] * np + j];
+#pragma unroll
+  for (int g = 0; g < PERMUTE_GROUP; ++g)
+    if (g < grp.n) scratch[(long long)g * nland + i] = v[g];
+}
+__global__ void permute_copyback_kernel(const float* __restrict__ scratch, float* __restrict__ state, PermuteGroup grp,
+                                        long long np, int nland) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nland) return;
+#pragma unroll
+  for (int g = 0; g < PERMUTE_GROUP; ++g)
+    if (g < grp.n) state[(long long)grp.plane[g] * np + i] = scratch[(long long)g * nland + i];
 }
 __global__ void permute_cell_kernel(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ perm,
                                     long long np, int nland) {
@@ -796,25 +907,41 @@ __global__ void permute_cell_kernel(const int* __restrict__ src, int* __restrict
   dst[i] = src[i < nland ? (long long)perm[i] : i];
 }
 
-static int rebin(noahmp_b200_ctx* ctx) {
+// Runs entirely in the order of stream `s` (the stream the steps run on): no device-wide synchronisation, the host
+// only swaps the two column-map buffers.
+static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
   const int nland = ctx->nclass[CL_LAND];
   const long long np = ctx->np;
   const int nch = ctx->bin_chunks;
   if (nland == 0 || nch == 0) return 0;
-  cudaStream_t s = ctx->stream;
+  if (ctx->last_step_stream && ctx->last_step_stream != s) {  // steps in flight on another stream: order after them
+    if (!ctx->ev_rebin) CK(cudaEventCreateWithFlags(&ctx->ev_rebin, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ev_rebin, ctx->last_step_stream));
+    CK(cudaStreamWaitEvent(s, ctx->ev_rebin, 0));
+  }
   if (!ctx->d_state2) {
-    CK(cudaMalloc(&ctx->d_state2, sizeof(float) * (size_t)NPLANES_ALLOC * (size_t)ctx->np_alloc));
+    CK(cudaMalloc(&ctx->d_state2, sizeof(float) * (size_t)PERMUTE_GROUP * (size_t)nland));
     CK(cudaMalloc(&ctx->d_cell2, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_keys, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_keys2, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_perm, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_iota, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_chunk, sizeof(int) * 80));
+    ctx->moved_planes.clear();
     std::vector<unsigned char> kind(NPLANES_ALLOC, 0);
     for (int f = 0; f < NFIELDS; ++f)
       for (int k = 0; k < kFields[f].layers; ++k) kind[kSlots.slot[f] + k] = (unsigned char)kFields[f].kind;
-    CK(cudaMalloc(&ctx->d_plane_kind, NPLANES_ALLOC));
-    CK(cudaMemcpy(ctx->d_plane_kind, kind.data(), NPLANES_ALLOC, cudaMemcpyHostToDevice));
+    for (int pl = 0; pl < NPLANES_ALLOC; ++pl)
+      if (kind[pl] == NMP_K_INOUT) ctx->moved_planes.push_back(pl);
+    size_t need = 0;
+    int bits = 5;
+    while ((1 << (bits - 5)) < 64) ++bits;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
+    if (need > ctx->cub_bytes) {
+      if (ctx->d_cub) CK(cudaFree(ctx->d_cub));
+      CK(cudaMalloc(&ctx->d_cub, need));
+      ctx->cub_bytes = need;
+    }
   }
   CK(cudaMemcpyAsync(ctx->d_chunk, ctx->ch_land.data(), sizeof(int) * (nch + 1), cudaMemcpyHostToDevice, s));
   const int T = 256;
@@ -822,25 +949,22 @@ static int rebin(noahmp_b200_ctx* ctx) {
   ctx->launches++;
   int bits = 5;
   while ((1 << (bits - 5)) < nch) ++bits;
-  size_t need = 0;
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
-  if (need > ctx->cub_bytes) {
-    if (ctx->d_cub) CK(cudaFree(ctx->d_cub));
-    CK(cudaMalloc(&ctx->d_cub, need));
-    ctx->cub_bytes = need;
-  }
+  size_t need = ctx->cub_bytes;
   // stable LSD radix sort: columns of equal key keep their current relative order
   CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
-  dim3 grid((unsigned)((np + T - 1) / T), (NPLANES_ALLOC + PERMUTE_GROUP - 1) / PERMUTE_GROUP);
-  permute_state_kernel<<<grid, T, 0, s>>>(ctx->d_state, ctx->d_state2, ctx->d_perm, ctx->d_plane_kind, np, nland,
-                                          NPLANES_ALLOC);
+  const unsigned nb = (unsigned)((nland + T - 1) / T);
+  for (size_t g0 = 0; g0 < ctx->moved_planes.size(); g0 += PERMUTE_GROUP) {
+    PermuteGroup grp;
+    grp.n = (int)std::min((size_t)PERMUTE_GROUP, ctx->moved_planes.size() - g0);
+    for (int g = 0; g < PERMUTE_GROUP; ++g) grp.plane[g] = g < grp.n ? ctx->moved_planes[g0 + g] : 0;
+    permute_state_kernel<<<nb, T, 0, s>>>(ctx->d_state, ctx->d_state2, ctx->d_perm, grp, np, nland);
+    permute_copyback_kernel<<<nb, T, 0, s>>>(ctx->d_state2, ctx->d_state, grp, np, nland);
+    ctx->launches += 2;
+  }
   permute_cell_kernel<<<(unsigned)((np + T - 1) / T), T, 0, s>>>(ctx->d_cell, ctx->d_cell2, ctx->d_perm, np, nland);
-  ctx->launches += 2;
+  ctx->launches++;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(s));
-  std::swap(ctx->d_state, ctx->d_state2);
   std::swap(ctx->d_cell, ctx->d_cell2);
-  ctx->base.state = ctx->d_state;
   ctx->base.cell = ctx->d_cell;
   ctx->binned = true;
   ctx->steps_since_rebin = 0;
@@ -861,6 +985,18 @@ static int h2d_rows(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, 
   return 0;
 }
 
+// gather of compact range [first, first+count) of one field (all its layers) from the grid-order staging
+__global__ void gather_range_kernel(const PlaneDesc* __restrict__ planes, const int* __restrict__ cell, float* state,
+                                    long long np, int ni, long long first, long long count) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= count) return;
+  n += first;
+  const PlaneDesc d = planes[blockIdx.y];
+  const int c = cell[n];
+  const int i = c % ni, j = c / ni;
+  state[(long long)d.plane * np + n] = d.grid[(long long)i + (long long)d.layer * ni + (long long)j * ni * d.layers];
+}
+
 // RESIDENT-mode step as a row-chunk pipeline: while chunk c is computed, the forcing rows of chunk c+1 are on
 // their way up and the requested result fields of chunk c-1 on their way down (three streams, events in between).
 // Columns of a class are stored in grid order, so a row chunk is one contiguous compact range per class.
@@ -876,7 +1012,7 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
     CK(cudaEventCreate(&ctx->ev_t0));
   }
   const unsigned evflags = ctx->trace ? cudaEventDefault : cudaEventDisableTiming;
-  while ((int)ctx->ev_in.size() < nchunks) {
+  while ((int)ctx->ev_in.size() < std::max(nchunks, 1)) {
     cudaEvent_t e1, e2, e3;
     CK(cudaEventCreateWithFlags(&e1, evflags));
     CK(cudaEventCreateWithFlags(&e2, evflags));
@@ -887,23 +1023,47 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
   }
   if (ctx->trace) CK(cudaEventRecord(ctx->ev_t0, ctx->s_in));
   struct Plane { int id; const float* src; int nk, lev; };
-  const Plane planes[NFORC] = {
+  const Plane all_planes[NFORC] = {
       {FC_COSZIN, a->coszin, 1, 1}, {FC_T, a->t3d, nk, 1},       {FC_QV, a->qv3d, nk, 1},      {FC_U, a->u_phy, nk, 1},
       {FC_V, a->v_phy, nk, 1},      {FC_SWDOWN, a->swdown, 1, 1}, {FC_GLW, a->glw, 1, 1},      {FC_P1, a->p8w3d, nk, a->kts},
       {FC_P2, a->p8w3d, nk, a->kts + 1}, {FC_RAINBL, a->rainbl, 1, 1}, {FC_VEGFRA, a->vegfra, 1, 1}, {FC_DZ8W, a->dz8w, nk, 1}};
-  if (upload)
-    for (const Plane& pl : planes) pin(ctx, pl.src, sizeof(float) * (size_t)ni * nj * pl.nk);
+  // Forcing planes the caller declared unchanged (noahmp_b200_set_forcing_hints) are not sent again once the device
+  // holds a copy; with P8W_LEVELS_EQUAL level 2 of P8W3D is read from the level-1 plane.
+  Plane planes[NFORC];
+  int nplanes = 0;
+  if (upload) {
+    for (const Plane& pl : all_planes) {
+      bool skip = false;
+      if (pl.id == FC_DZ8W && (ctx->hints & NOAHMP_HINT_DZ8W_CONSTANT) && ctx->forc_valid[FC_DZ8W]) skip = true;
+      if (pl.id == FC_VEGFRA && (ctx->hints & NOAHMP_HINT_VEGFRA_UNCHANGED) && ctx->forc_valid[FC_VEGFRA]) skip = true;
+      if (pl.id == FC_P2 && (ctx->hints & NOAHMP_HINT_P8W_LEVELS_EQUAL)) skip = true;
+      if (!skip) planes[nplanes++] = pl;
+    }
+    for (int k = 0; k < nplanes; ++k) pin(ctx, planes[k].src, sizeof(float) * (size_t)ni * nj * planes[k].nk);
+  }
   for (int f : ctx->fetch) pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
+  for (int f : ctx->push) {
+    if (!host_ptr(a, f)) { set_error(std::string("null array in the push list: ") + kFields[f].name); return NOAHMP_ERR_ARG; }
+    pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
+  }
 
   // host forcing supersedes device pointers bound earlier with bind_forcing()
-  if (upload)
+  if (upload) {
     for (int f = 0; f < NFORC; ++f) ctx->base.forc[f] = ctx->d_forc[f];
+    if (ctx->hints & NOAHMP_HINT_P8W_LEVELS_EQUAL) ctx->base.forc[FC_P2] = ctx->d_forc[FC_P1];
+  }
   StepParams p = ctx->base;
   p.itimestep = a->itimestep;
   p.yearlen = year_length(a->yr);
   p.julian = a->julian;
   p.dt = a->dt;
   cudaStream_t sk = ctx->stream;
+  if (ctx->last_step_stream && ctx->last_step_stream != sk) {  // device-side steps issued earlier on a caller stream
+    if (!ctx->ev_rebin) CK(cudaEventCreateWithFlags(&ctx->ev_rebin, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ev_rebin, ctx->last_step_stream));
+    CK(cudaStreamWaitEvent(sk, ctx->ev_rebin, 0));
+  }
+  ctx->last_step_stream = sk;
   CK(cudaMemsetAsync(ctx->d_errkey, 0xff, sizeof(unsigned long long), sk));
   CK(cudaMemsetAsync(ctx->d_errcount, 0, sizeof(int), sk));
   if (a->itimestep == 1 && ctx->nclass[CL_WATER] > 0) {
@@ -914,20 +1074,33 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
     ctx->launches++;
   }
   const int nland = ctx->nclass[CL_LAND];
-  int rc0 = chunk_ranges(ctx, nchunks);
-  if (rc0) return rc0;
+  int rc0;
   if (ctx->rebin_interval > 0 && nland > 0 && a->itimestep > 1 &&
       (!ctx->binned ? ctx->steps_since_rebin >= 2 : ctx->steps_since_rebin >= ctx->rebin_interval)) {
-    if ((rc0 = rebin(ctx))) return rc0;
+    if ((rc0 = chunk_ranges(ctx, ctx->binned ? ctx->bin_chunks : auto_chunks(ctx), nullptr))) return rc0;
+    if ((rc0 = rebin(ctx, sk))) return rc0;
     p.state = ctx->d_state;
     p.cell = ctx->d_cell;
   }
+  ChunkRanges R;
+  if ((rc0 = chunk_ranges(ctx, nchunks, &R))) return rc0;
+  nchunks = R.n;
   ctx->steps_since_rebin++;
+  const int T = 256;
   for (int c = 0; c < nchunks; ++c) {
-    const int j0 = chunk_row(ctx, c, nchunks), j1 = chunk_row(ctx, c + 1, nchunks);
+    const int j0 = R.row[c], j1 = R.row[c + 1];
     if (j1 <= j0) continue;
-    if (upload) {
-      for (const Plane& pl : planes) {
+    StepRange r;
+    r.land_first = R.land[c];
+    r.land_count = R.land[c + 1] - r.land_first;
+    r.glac_first = R.glac[c];
+    r.glac_count = R.glac[c + 1] - r.glac_first;
+    const int s0 = R.sea[c], s1 = R.sea[c + 1];
+    const int rng[3][2] = {{r.land_first, r.land_count}, {r.glac_first, r.glac_count}, {s0, s1 - s0}};
+    bool waited = false;
+    if (upload && nplanes > 0) {
+      for (int k = 0; k < nplanes; ++k) {
+        const Plane& pl = planes[k];
         int rc = h2d_rows(ctx, ctx->d_forc[pl.id], pl.src, pl.nk, kms, pl.lev, j0, j1, ctx->s_in);
         if (rc) return rc;
         if (ctx->trace && c == 0) {
@@ -936,35 +1109,45 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
           CK(cudaEventRecord(ctx->ev_plane[pl.id], ctx->s_in));
         }
       }
+      waited = true;
+    }
+    // INOUT arrays the driver rewrites before every call (e.g. XLAIXY from the forcing file): rows up, then into
+    // the compact planes of this chunk's columns
+    for (int f : ctx->push) {
+      const size_t L = kFields[f].layers, off = (size_t)j0 * ni * L, cnt = (size_t)(j1 - j0) * ni * L;
+      CK(cudaMemcpyAsync(ctx->d_grid[f] + off, host_ptr(a, f) + off, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->s_in));
+      waited = true;
+    }
+    if (waited) {
       CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
       CK(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
     }
-    StepRange r;
-    r.land_first = ctx->ch_land[c];
-    r.land_count = ctx->ch_land[c + 1] - r.land_first;
-    r.glac_first = ctx->ch_glac[c];
-    r.glac_count = ctx->ch_glac[c + 1] - r.glac_first;
+    for (int f : ctx->push) {
+      for (auto& q : rng) {
+        if (q[1] <= 0) continue;
+        dim3 grid((unsigned)((q[1] + T - 1) / T), kFields[f].layers);
+        gather_range_kernel<<<grid, T, 0, sk>>>(ctx->d_planes + kSlots.slot[f], p.cell, ctx->d_state, ctx->np, ctx->ni,
+                                                (long long)q[0], (long long)q[1]);
+        ctx->launches++;
+      }
+    }
     const char* v = ctx->math_mode == NOAHMP_MATH_PARITY ? nmp_launch_step_parity(p, r, sk, &ctx->launches)
                                                          : nmp_launch_step_fast(p, r, sk, &ctx->launches);
     ctx->variant = v;
-    const int s0 = ctx->ch_sea[c], s1 = ctx->ch_sea[c + 1];
     if (s1 > s0) {
-      seaice_kernel<<<(s1 - s0 + 255) / 256, 256, 0, sk>>>(ctx->d_state, ctx->d_cell, ctx->d_stat[ST_XICE], ctx->np, s0,
+      seaice_kernel<<<(s1 - s0 + 255) / 256, 256, 0, sk>>>(ctx->d_state, p.cell, ctx->d_stat[ST_XICE], ctx->np, s0,
                                                          s1 - s0, a->itimestep);
       ctx->launches++;
     }
     if (!ctx->fetch.empty()) {
-      // scatter the requested fields of this chunk's columns into the grid-order staging, then send the rows down
-      const int T = 256;
-      const int rng[3][2] = {{r.land_first, r.land_count}, {r.glac_first, r.glac_count}, {s0, s1 - s0}};
-      for (int f : ctx->fetch) {
-        for (auto& q : rng) {
-          if (q[1] <= 0) continue;
-          dim3 grid((unsigned)((q[1] + T - 1) / T), kFields[f].layers);
-          scatter_kernel<<<grid, T, 0, sk>>>(ctx->d_planes + kSlots.slot[f], ctx->d_cell, ctx->d_state, ctx->np, ctx->ni,
-                                              (long long)q[0], (long long)q[1]);
-          ctx->launches++;
-        }
+      // scatter the requested fields of this chunk's columns into the grid-order staging (one launch per class
+      // range for the whole fetch list), then send the rows down
+      for (auto& q : rng) {
+        if (q[1] <= 0) continue;
+        dim3 grid((unsigned)((q[1] + T - 1) / T), ctx->n_fetch_planes);
+        scatter_kernel<<<grid, T, 0, sk>>>(ctx->d_fetch_planes, p.cell, ctx->d_state, ctx->np, ctx->ni, (long long)q[0],
+                                            (long long)q[1]);
+        ctx->launches++;
       }
       CK(cudaEventRecord(ctx->ev_k[c], sk));
       CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
@@ -979,34 +1162,29 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
     }
   }
   CK(cudaGetLastError());
+  if (ctx->budget_on && (rc0 = budget_accumulate(ctx, a->dt, sk))) return rc0;
+  if (upload)
+    for (int k = 0; k < nplanes; ++k) ctx->forc_valid[planes[k].id] = true;
   CK(cudaMemcpyAsync(ctx->h_errkey, ctx->d_errkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sk));
   CK(cudaMemcpyAsync(ctx->h_errcount, ctx->d_errcount, sizeof(int), cudaMemcpyDeviceToHost, sk));
   const auto t_enq = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(sk));
   if (!ctx->fetch.empty()) CK(cudaStreamSynchronize(ctx->s_out));
   if (ctx->trace) {
-    fprintf(stderr, "[noahmp_b200 trace] host: enqueue %.2f ms, total %.2f ms\n",
+    fprintf(stderr, "[noahmp_b200 trace] host: enqueue %.2f ms, total %.2f ms (%d chunks, %d forcing planes up)\n",
             std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), nchunks,
+            upload ? nplanes : 0);
     // completion times (ms after the call's first enqueue): forcing rows up | physics (+ scatter) | results down
     fprintf(stderr, "[noahmp_b200 trace] step %d:", a->itimestep);
     for (int c = 0; c < nchunks; ++c) {
       float t[3] = {-1.f, -1.f, -1.f};
-      if (upload) cudaEventElapsedTime(&t[0], ctx->ev_t0, ctx->ev_in[c]);
+      if (upload && nplanes > 0) cudaEventElapsedTime(&t[0], ctx->ev_t0, ctx->ev_in[c]);
       cudaEventElapsedTime(&t[1], ctx->ev_t0, ctx->ev_k[c]);
       if (!ctx->fetch.empty()) cudaEventElapsedTime(&t[2], ctx->ev_t0, ctx->ev_out[c]);
       fprintf(stderr, " [%d] %.2f|%.2f|%.2f", c, t[0], t[1], t[2]);
     }
     fprintf(stderr, "\n");
-    if (upload && !ctx->ev_plane.empty()) {
-      fprintf(stderr, "[noahmp_b200 trace] chunk 0 forcing planes up at:");
-      for (int f = 0; f < NFORC; ++f) {
-        float t = -1.f;
-        if (ctx->ev_plane[f]) cudaEventElapsedTime(&t, ctx->ev_t0, ctx->ev_plane[f]);
-        fprintf(stderr, " %.2f", t);
-      }
-      fprintf(stderr, "\n");
-    }
     cudaGetLastError();
   }
   return 0;
@@ -1035,10 +1213,59 @@ static int parse_fields(const char* fields, std::vector<int>& list) {
 }
 int noahmp_b200_set_fetch(noahmp_b200_ctx* ctx, const char* fields) {
   if (!ctx || !fields) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
   std::vector<int> list;
   int rc = parse_fields(fields, list);
   if (rc) return rc;
+  if ((rc = build_plane_descs(ctx))) return rc;
+  std::vector<PlaneDesc> h;
+  for (int f : list)
+    for (int k = 0; k < kFields[f].layers; ++k) h.push_back({ctx->d_grid[f], kSlots.slot[f] + k, k, kFields[f].layers});
+  CK(cudaStreamSynchronize(ctx->stream));  // a call in flight may still read the old descriptor list
+  if (ctx->d_fetch_planes) { CK(cudaFree(ctx->d_fetch_planes)); ctx->d_fetch_planes = nullptr; }
+  if (!h.empty()) {
+    CK(cudaMalloc(&ctx->d_fetch_planes, sizeof(PlaneDesc) * h.size()));
+    CK(cudaMemcpy(ctx->d_fetch_planes, h.data(), sizeof(PlaneDesc) * h.size(), cudaMemcpyHostToDevice));
+  }
+  ctx->n_fetch_planes = (int)h.size();
   ctx->fetch = list;
+  return 0;
+}
+
+// RESIDENT mode: INOUT fields (comma separated member names, "" = none) whose HOST content every noahmplsm call
+// takes again before the step.  The HRLDAS driver overwrites LAI (= XLAIXY) from the forcing file before every call
+// (module_hrldas_noahmp_driver.F90:335, driver/module_hrldas_netcdf_io.F90:1365/1402), so a resident drop-in must
+// list "xlaixy" here to follow the reference when that array is rewritten between calls.
+int noahmp_b200_set_push(noahmp_b200_ctx* ctx, const char* fields) {
+  if (!ctx || !fields) return NOAHMP_ERR_ARG;
+  std::vector<int> list;
+  int rc = parse_fields(fields, list);
+  if (rc) return rc;
+  for (int f : list)
+    if (kFields[f].kind != NMP_K_INOUT) { set_error(std::string("set_push: not an INOUT array: ") + kFields[f].name); return NOAHMP_ERR_ARG; }
+  ctx->push = list;
+  return 0;
+}
+
+// Forcing planes that need no upload in the following RESIDENT-mode calls (NOAHMP_HINT_* bits, see the header).
+int noahmp_b200_set_forcing_hints(noahmp_b200_ctx* ctx, unsigned hints) {
+  if (!ctx || (hints & ~(unsigned)(NOAHMP_HINT_DZ8W_CONSTANT | NOAHMP_HINT_VEGFRA_UNCHANGED | NOAHMP_HINT_P8W_LEVELS_EQUAL)))
+    return NOAHMP_ERR_ARG;
+  // a hint that is withdrawn makes the next call upload the plane again
+  if (!(hints & NOAHMP_HINT_DZ8W_CONSTANT)) ctx->forc_valid[FC_DZ8W] = false;
+  if (!(hints & NOAHMP_HINT_VEGFRA_UNCHANGED)) ctx->forc_valid[FC_VEGFRA] = false;
+  ctx->hints = hints;
+  return 0;
+}
+
+// Release the page-lock the library holds on a caller array (see noahmp_b200_create); a no-op for unknown pointers.
+int noahmp_b200_unpin(noahmp_b200_ctx* ctx, const void* host_ptr_) {
+  if (!ctx || !host_ptr_) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->registered.count(host_ptr_)) {
+    CK(cudaDeviceSynchronize());
+    unpin_one(ctx, host_ptr_);
+  }
   return 0;
 }
 
@@ -1151,6 +1378,7 @@ int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks) {
 
 int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp_status* status) {
   if (!ctx || !a) return NOAHMP_ERR_ARG;
+  ++ctx->pin_clock;
   CK(cudaSetDevice(ctx->device));
   int rc;
   if (ctx->sync_mode == NOAHMP_SYNC_FULL || !ctx->uploaded) {
@@ -1160,15 +1388,13 @@ int noahmp_b200_noahmplsm(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp
     if ((rc = check_bounds(ctx, a))) return rc;
     fill_scalars(ctx, a);
     if ((rc = check_options(ctx))) return rc;
-    int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 9 : 1);
-    if (nch > ctx->nj) nch = ctx->nj;
-    if ((rc = step_resident_pipelined(ctx, a, nch))) return rc;
+    if ((rc = step_resident_pipelined(ctx, a, auto_chunks(ctx)))) return rc;
     noahmp_status st;
     decode_status(ctx, &st);
     if (status) *status = st;
     return st.code;
   }
-  if ((rc = noahmp_b200_step_device(ctx, a->itimestep, a->yr, a->julian, a->dt, nullptr))) return rc;
+  if ((rc = step_device_impl(ctx, a->itimestep, a->yr, a->julian, a->dt, nullptr, /*clear_latch=*/true))) return rc;
   if (ctx->sync_mode == NOAHMP_SYNC_FULL) {
     if ((rc = scatter_fields(ctx))) return rc;
     if ((rc = download_state(ctx, a))) return rc;
@@ -1300,10 +1526,9 @@ static void wt_params(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a, WtParam
   for (int k = 0; k < NOAHMP_NSOIL; ++k) w.dzs[k] = a->dzs[k];
 }
 
-int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
-  int rc = wt_check(ctx, a);
-  if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+// allocation and the uploads that happen once (static inputs, accumulators) or on every call in SYNC_FULL mode
+static int wt_prepare(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  int rc;
   const size_t plane = sizeof(float) * ctx->ncell, halo = sizeof(float) * (size_t)(ctx->ni + 2) * (ctx->nj + 2);
   if (!ctx->d_kcell) {
     for (int k = 0; k < NWT; ++k) {
@@ -1324,8 +1549,56 @@ int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) 
     CK(cudaMemcpyAsync(ctx->d_grid[F_smoiseq], a->smoiseq, plane * NOAHMP_NSOIL, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = gather_field(ctx, F_smoiseq))) return rc;
     ctx->wt_init = true;
+    CK(cudaStreamSynchronize(ctx->stream));
   }
-  if (full) {
+  return 0;
+}
+
+// LATERALFLOW pass 1 on stream s: WTD of every cell in grid order, then KCELL / HEAD with an empty ring
+static int wt_enqueue_head(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a, cudaStream_t s) {
+  const size_t halo = sizeof(float) * (size_t)(ctx->ni + 2) * (ctx->nj + 2);
+  if (ctx->np > 0) {
+    const int T = 256;
+    dim3 grid((unsigned)((ctx->np + T - 1) / T), 1);
+    scatter_kernel<<<grid, T, 0, s>>>(ctx->d_planes + kSlots.slot[F_zwtxy], ctx->d_cell, ctx->d_state, ctx->np, ctx->ni);
+    ctx->launches++;
+  }
+  CK(cudaMemsetAsync(ctx->d_kcell, 0, halo, s));
+  CK(cudaMemsetAsync(ctx->d_head, 0, halo, s));
+  WtParams w;
+  wt_params(ctx, a, w);
+  if (ctx->math_mode == NOAHMP_MATH_PARITY) nmp_launch_wtable_parity(w, s, &ctx->launches, 0);
+  else nmp_launch_wtable_fast(w, s, &ctx->launches, 0);
+  CK(cudaGetLastError());
+  return 0;
+}
+// pass 2 + river flux + UPDATEWTD per land column, bookkeeping of the other cells, on stream s
+static int wt_enqueue_columns(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a, cudaStream_t s) {
+  WtParams w;
+  wt_params(ctx, a, w);
+  if (ctx->math_mode == NOAHMP_MATH_PARITY) nmp_launch_wtable_parity(w, s, &ctx->launches, 1);
+  else nmp_launch_wtable_fast(w, s, &ctx->launches, 1);
+  const int T = 256;
+  wt_nonland_cells_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, s>>>(
+      ctx->d_class, ctx->d_wt[WT_QRF], ctx->d_wt[WT_QSPRING], ctx->d_grid[F_rechxy], ctx->d_grid[F_deeprechxy], ctx->ncell);
+  ctx->launches++;
+  const int nother = (int)ctx->np - ctx->nclass[CL_LAND];
+  if (nother > 0) {
+    wt_nonland_cols_kernel<<<(nother + T - 1) / T, T, 0, s>>>(ctx->d_state, ctx->np, ctx->nclass[CL_LAND], nother);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
+  int rc = wt_check(ctx, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  ++ctx->pin_clock;
+  if ((rc = wt_prepare(ctx, a))) return rc;
+  const size_t plane = sizeof(float) * ctx->ncell;
+  if (ctx->sync_mode == NOAHMP_SYNC_FULL) {
     for (const WtField& wf : kWtInout) {
       const size_t bytes = plane * kFields[wf.f].layers;
       pin(ctx, wt_ptr(a, wf.off), bytes);
@@ -1334,15 +1607,8 @@ int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) 
     }
   } else {
     CK(cudaDeviceSynchronize());  // resident steps may have run on a caller stream
-    if ((rc = scatter_field(ctx, F_zwtxy))) return rc;  // WTD of every cell in grid order for the stencil
   }
-  CK(cudaMemsetAsync(ctx->d_kcell, 0, halo, ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_head, 0, halo, ctx->stream));
-  WtParams w;
-  wt_params(ctx, a, w);
-  if (ctx->math_mode == NOAHMP_MATH_PARITY) nmp_launch_wtable_parity(w, ctx->stream, &ctx->launches, 0);
-  else nmp_launch_wtable_fast(w, ctx->stream, &ctx->launches, 0);
-  CK(cudaGetLastError());
+  if ((rc = wt_enqueue_head(ctx, a, ctx->stream))) return rc;
   CK(cudaStreamSynchronize(ctx->stream));  // the halo exchange that may follow runs on the caller's stream
   return 0;
 }
@@ -1379,29 +1645,150 @@ int noahmp_b200_wtable_end(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
   if (!ctx->d_kcell) { set_error("wtable_end before wtable_begin"); return NOAHMP_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   CK(cudaDeviceSynchronize());  // halo writes of the caller are complete
-  WtParams w;
-  wt_params(ctx, a, w);
-  if (ctx->math_mode == NOAHMP_MATH_PARITY) nmp_launch_wtable_parity(w, ctx->stream, &ctx->launches, 1);
-  else nmp_launch_wtable_fast(w, ctx->stream, &ctx->launches, 1);
-  const int T = 256;
-  wt_nonland_cells_kernel<<<(unsigned)((ctx->ncell + T - 1) / T), T, 0, ctx->stream>>>(
-      ctx->d_class, ctx->d_wt[WT_QRF], ctx->d_wt[WT_QSPRING], ctx->d_grid[F_rechxy], ctx->d_grid[F_deeprechxy], ctx->ncell);
-  ctx->launches++;
-  const int nother = (int)ctx->np - ctx->nclass[CL_LAND];
-  if (nother > 0) {
-    wt_nonland_cols_kernel<<<(nother + T - 1) / T, T, 0, ctx->stream>>>(ctx->d_state, ctx->np, ctx->nclass[CL_LAND], nother);
-    ctx->launches++;
-  }
-  CK(cudaGetLastError());
+  if ((rc = wt_enqueue_columns(ctx, a, ctx->stream))) return rc;
   if (ctx->sync_mode == NOAHMP_SYNC_FULL) return wt_download(ctx, a);
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
+// Halo exchange of KCELL / HEAD with the neighbouring tiles over the context's communicator (between _begin and _end)
+int noahmp_b200_wtable_exchange(noahmp_b200_ctx* ctx, void* stream) {
+  if (!ctx || !ctx->d_kcell) { set_error("wtable_exchange before wtable_begin"); return NOAHMP_ERR_ARG; }
+  if (!ctx->comm.comm || ctx->comm.nranks == 1) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  return halo_exchange(ctx->comm, ctx->d_kcell, ctx->d_head, ctx->ni, ctx->nj, s, &ctx->launches);
+}
+
+// CALL WTABLE_mmf_noahmp(...): with a communicator (noahmp_b200_comm_init) the halo is exchanged inside the call
 int noahmp_b200_wtable(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
   int rc = noahmp_b200_wtable_begin(ctx, a);
   if (rc) return rc;
+  if ((rc = noahmp_b200_wtable_exchange(ctx, nullptr))) return rc;
   return noahmp_b200_wtable_end(ctx, a);
+}
+
+// The same call for a device-side stepping loop (RESIDENT mode): everything — pass 1, the NCCL halo, pass 2 and the
+// column update — is enqueued on `stream` behind the step that precedes it; the host does not wait.
+int noahmp_b200_wtable_device(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a, void* stream) {
+  int rc = wt_check(ctx, a);
+  if (rc) return rc;
+  if (ctx->sync_mode != NOAHMP_SYNC_RESIDENT) { set_error("wtable_device needs RESIDENT mode"); return NOAHMP_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->wt_init && (rc = wt_prepare(ctx, a))) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  if (ctx->last_step_stream && ctx->last_step_stream != s) {
+    if (!ctx->ev_rebin) CK(cudaEventCreateWithFlags(&ctx->ev_rebin, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ev_rebin, ctx->last_step_stream));
+    CK(cudaStreamWaitEvent(s, ctx->ev_rebin, 0));
+  }
+  ctx->last_step_stream = s;
+  if ((rc = wt_enqueue_head(ctx, a, s))) return rc;
+  if (ctx->comm.comm && ctx->comm.nranks > 1 &&
+      (rc = halo_exchange(ctx->comm, ctx->d_kcell, ctx->d_head, ctx->ni, ctx->nj, s, &ctx->launches))) return rc;
+  return wt_enqueue_columns(ctx, a, s);
+}
+
+// ---- communicator ---------------------------------------------------------------------------------------------------
+// rank 0 calls comm_unique_id and the host program hands the 128 bytes to every rank (MPI_Bcast in the Fortran driver,
+// torch.distributed.broadcast under torchrun); then every rank calls comm_init.  Ranks are laid out as
+// mpp_land_partition does: rank = iprocx + iprocy * nprocx (mpp/module_mpp_land.F90:83-84).
+int noahmp_b200_comm_unique_id(void* id128) {
+  if (!id128) return NOAHMP_ERR_ARG;
+  NcclApi* N = nccl_api();
+  if (!N) { set_error("libnccl.so.2 not found (set NOAHMP_B200_NCCL to its path)"); return NOAHMP_ERR_CUDA; }
+  ncclUniqueId id;
+  NK(N->GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int noahmp_b200_comm_init(noahmp_b200_ctx* ctx, const void* id128, int rank, int nranks) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return NOAHMP_ERR_ARG;
+  NcclApi* N = nccl_api();
+  if (!N) { set_error("libnccl.so.2 not found (set NOAHMP_B200_NCCL to its path)"); return NOAHMP_ERR_CUDA; }
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm.comm) { N->CommDestroy(ctx->comm.comm); ctx->comm.comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NK(N->CommInitRank(&ctx->comm.comm, nranks, id, rank));
+  NmpComm& C = ctx->comm;
+  C.rank = rank; C.nranks = nranks;
+  int npx, npy;
+  noahmp_b200_proc_grid(nranks, &npx, &npy);
+  const int ipx = rank % npx, ipy = rank / npx;
+  C.left = ipx > 0 ? rank - 1 : -1;
+  C.right = ipx < npx - 1 ? rank + 1 : -1;
+  C.down = ipy > 0 ? rank - npx : -1;
+  C.up = ipy < npy - 1 ? rank + npx : -1;
+  if (!C.d_send) {
+    CK(cudaMalloc(&C.d_send, sizeof(float) * 4 * (size_t)ctx->nj));
+    CK(cudaMalloc(&C.d_recv, sizeof(float) * 4 * (size_t)ctx->nj));
+    CK(cudaMalloc(&C.d_budget_sum, sizeof(double) * NBUDGET));
+  }
+  return 0;
+}
+
+int noahmp_b200_comm_neighbours(const noahmp_b200_ctx* ctx, int nb[4]) {
+  if (!ctx || !nb) return NOAHMP_ERR_ARG;
+  nb[0] = ctx->comm.left; nb[1] = ctx->comm.right; nb[2] = ctx->comm.down; nb[3] = ctx->comm.up;
+  return 0;
+}
+
+// ---- global water / energy budget (nmp_comm.cuh: budget_kernel) -----------------------------------------------------
+int noahmp_b200_budget_enable(noahmp_b200_ctx* ctx, int enable) {
+  if (!ctx) return NOAHMP_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (enable && !ctx->d_budget) CK(cudaMalloc(&ctx->d_budget, sizeof(double) * NBUDGET));
+  if (enable) {
+    CK(cudaMemset(ctx->d_budget, 0, sizeof(double) * NBUDGET));
+    ctx->budget_steps = 0;
+  }
+  ctx->budget_on = enable != 0;
+  return 0;
+}
+
+// called behind every step when the budget is enabled
+static int budget_accumulate(noahmp_b200_ctx* ctx, float dt, cudaStream_t s) {
+  const int ncol = ctx->nclass[CL_LAND] + ctx->nclass[CL_GLACIER];
+  ctx->budget_steps++;
+  if (ncol == 0) return 0;
+  // the instantaneous sums restart with every step
+  CK(cudaMemsetAsync(ctx->d_budget, 0, sizeof(double), s));
+  CK(cudaMemsetAsync(ctx->d_budget + 5, 0, sizeof(double), s));
+  const StepParams& b = ctx->base;
+  const float dz0 = -b.zsoil[0], dz1 = b.zsoil[0] - b.zsoil[1], dz2 = b.zsoil[1] - b.zsoil[2], dz3 = b.zsoil[2] - b.zsoil[3];
+  const int T = 256;
+  budget_kernel<<<(ncol + T - 1) / T, T, 0, s>>>(ctx->d_state, b.forc[FC_RAINBL], ctx->d_cell, ctx->np, ctx->nclass[CL_LAND],
+                                                 ncol, dt, dz0, dz1, dz2, dz3, ctx->d_budget);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// out[8] as listed in nmp_comm.cuh; global != 0 sums over the ranks of the communicator (one ncclAllReduce of 8 fp64).
+// reset != 0 starts a new accumulation interval.
+int noahmp_b200_budget_read(noahmp_b200_ctx* ctx, double* out, int global, int reset) {
+  if (!ctx || !out || !ctx->d_budget) { set_error("budget_read before budget_enable"); return NOAHMP_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->last_step_stream ? ctx->last_step_stream : ctx->stream;
+  const double tail[2] = {(double)(ctx->nclass[CL_LAND] + ctx->nclass[CL_GLACIER]), (double)ctx->budget_steps};
+  CK(cudaMemcpyAsync(ctx->d_budget + 6, tail, sizeof(tail), cudaMemcpyHostToDevice, s));
+  const double* src = ctx->d_budget;
+  if (global && ctx->comm.comm && ctx->comm.nranks > 1) {
+    NcclApi* N = nccl_api();
+    NK(N->AllReduce(ctx->d_budget, ctx->comm.d_budget_sum, NBUDGET, ncclFloat64, ncclSum, ctx->comm.comm, s));
+    src = ctx->comm.d_budget_sum;
+  }
+  CK(cudaMemcpyAsync(out, src, sizeof(double) * NBUDGET, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (global && ctx->comm.nranks > 1) out[7] /= ctx->comm.nranks;  // every rank counted the same steps
+  if (reset) {
+    CK(cudaMemsetAsync(ctx->d_budget, 0, sizeof(double) * NBUDGET, s));
+    ctx->budget_steps = 0;
+  }
+  return 0;
 }
 
 int noahmp_b200_wtable_sync_host(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
@@ -1446,6 +1833,7 @@ int noahmp_b200_forcing_static(noahmp_b200_ctx* ctx, const float* lat2d, const f
 
 int noahmp_b200_forcing_upload(noahmp_b200_ctx* ctx, int slot, const noahmp_forcing_fields* f) {
   if (!ctx || !f || slot < 0 || slot > 1) return NOAHMP_ERR_ARG;
+  ++ctx->pin_clock;
   CK(cudaSetDevice(ctx->device));
   int rc = fb_alloc(ctx);
   if (rc) return rc;
@@ -1517,6 +1905,7 @@ int noahmp_b200_forcing_apply(noahmp_b200_ctx* ctx, float fraction, int iday, in
 
 int noahmp_b200_noahmplsm_device_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, noahmp_status* status) {
   if (!ctx || !a) return NOAHMP_ERR_ARG;
+  ++ctx->pin_clock;
   if (ctx->sync_mode != NOAHMP_SYNC_RESIDENT || !ctx->uploaded) {
     set_error("noahmplsm_device_forcing needs RESIDENT mode and an uploaded state");
     return NOAHMP_ERR_ARG;
@@ -1526,9 +1915,8 @@ int noahmp_b200_noahmplsm_device_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_
   if ((rc = check_bounds(ctx, a))) return rc;
   fill_scalars(ctx, a);
   if ((rc = check_options(ctx))) return rc;
-  int nch = ctx->nchunks ? ctx->nchunks : (ctx->ncell >= (1LL << 20) ? 9 : 1);
-  if (nch > ctx->nj) nch = ctx->nj;
-  if (ctx->fetch.empty()) nch = 1;
+  int nch = auto_chunks(ctx);
+  if (ctx->fetch.empty() && ctx->push.empty()) nch = 1;  // nothing to overlap the physics with
   if ((rc = step_resident_pipelined(ctx, a, nch, /*upload=*/false))) return rc;
   noahmp_status st;
   decode_status(ctx, &st);

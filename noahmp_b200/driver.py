@@ -3,6 +3,7 @@
 Arrays use the reference's Fortran memory layout, expressed as C-contiguous numpy arrays of shape
 (nj[, k], ni) (see _capi.array_shape); scalars carry the names of the `noahmplsm` dummy arguments.
 """
+import collections
 import ctypes as C
 
 import numpy as np
@@ -11,6 +12,8 @@ from . import _capi, _lib
 
 SYNC_FULL, SYNC_RESIDENT = 0, 1
 MATH_FAST, MATH_PARITY = 0, 1
+HINT_DZ8W_CONSTANT, HINT_VEGFRA_UNCHANGED, HINT_P8W_LEVELS_EQUAL = 1, 2, 4
+HOLD_BUDGET_BYTES = 64 << 30  # arrays kept referenced (and page-locked by the library) per model, least recently used out
 
 # messages the reference passes to wrf_error_fatal for each status code (include/noahmp_b200.h)
 ERROR_TEXT = {
@@ -49,6 +52,33 @@ def tile(global_nx, global_ny, nproc, rank):
     return tuple(x.value for x in v)
 
 
+def bind_numa(device):
+    """Pin this process's threads to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned host
+    buffers it first-touches and the copies it drives stay on that node.  One process per GPU; a no-op when the
+    topology cannot be read.  Returns the node or None."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{pci}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class _DevArray:
     """Zero-copy view of a device plane for torch.as_tensor / cupy (CUDA array interface v2)."""
 
@@ -71,22 +101,40 @@ class NoahMP:
             raise NoahmpError(100, self._L.noahmp_b200_last_error().decode())
         self.set_mode(sync)
         self.set_math(math)
-        self._held = {}
+        self._held = collections.OrderedDict()
+        self._held_bytes = 0
 
     def _hold(self, arrays):
         """The library page-locks caller arrays of 4 MiB and more and remembers them by address (a Fortran driver's
         arrays live as long as the run).  numpy would unmap a freed array while it is still registered, so arrays of
-        that size stay referenced until close()."""
+        that size stay referenced here; a loop that passes fresh arrays to every call is bounded: beyond
+        HOLD_BUDGET_BYTES the least recently used ones are un-pinned (noahmp_b200_unpin) and released."""
         for v in (arrays.values() if isinstance(arrays, dict) else arrays):
             if isinstance(v, np.ndarray) and v.nbytes >= (4 << 20):
-                self._held[v.ctypes.data] = v
+                key = v.ctypes.data
+                if key in self._held:
+                    self._held.move_to_end(key)
+                else:
+                    self._held[key] = v
+                    self._held_bytes += v.nbytes
+        if self._held_bytes > HOLD_BUDGET_BYTES:
+            live = {v.ctypes.data for v in (arrays.values() if isinstance(arrays, dict) else arrays)
+                    if isinstance(v, np.ndarray)}
+            for key in list(self._held):
+                if self._held_bytes <= HOLD_BUDGET_BYTES:
+                    break
+                if key in live:
+                    continue
+                self._L.noahmp_b200_unpin(self._ctx, key)
+                self._held_bytes -= self._held.pop(key).nbytes
         return arrays
 
     def close(self):
         if getattr(self, "_ctx", None):
             self._L.noahmp_b200_destroy(self._ctx)
             self._ctx = None
-            self._held = {}
+            self._held = collections.OrderedDict()
+            self._held_bytes = 0
 
     __del__ = close
 
@@ -107,6 +155,27 @@ class NoahMP:
         a = _capi.make_args(self._hold(arrays), scalars)
         st = _capi.NoahmpStatus()
         self._check(self._L.noahmp_b200_noahmplsm(self._ctx, C.byref(a), C.byref(st)))
+        return st
+
+    def prepare(self, arrays, scalars):
+        """Marshal the 158-member argument list once; noahmplsm_prepared() then only patches what changes per step
+        (a Fortran caller builds the struct in the shim for free, ctypes needs ~0.5 ms for it)."""
+        return [_capi.make_args(self._hold(arrays), scalars), dict(arrays)]
+
+    def noahmplsm_prepared(self, prep, itimestep, yr, julian, forcing=None, device_forcing=False):
+        """noahmplsm() with a prepared argument list: `forcing` = dict of the arrays that are different objects this
+        step (names of the noahmplsm dummy arguments); device_forcing: the planes filled by forcing_apply() are used
+        (noahmplsm_device_forcing)."""
+        a, keep = prep
+        a.itimestep, a.yr, a.julian = int(itimestep), int(yr), float(julian)
+        if forcing:
+            self._hold(forcing)
+            for n, arr in forcing.items():
+                setattr(a, n, arr.ctypes.data_as(_capi.ARG_POINTER_TYPE[n]))
+                keep[n] = arr
+        st = _capi.NoahmpStatus()
+        fn = self._L.noahmp_b200_noahmplsm_device_forcing if device_forcing else self._L.noahmp_b200_noahmplsm
+        self._check(fn(self._ctx, C.byref(a), C.byref(st)))
         return st
 
     def sync_host(self, arrays, scalars):
@@ -135,6 +204,16 @@ class NoahMP:
     def set_fetch(self, fields=()):
         """Fields every RESIDENT-mode noahmplsm() call refreshes on the host (pipelined with the step)."""
         self._check(self._L.noahmp_b200_set_fetch(self._ctx, ",".join(fields).encode()))
+
+    def set_push(self, fields=()):
+        """INOUT fields whose host content every RESIDENT-mode noahmplsm() call takes again before the step (the HRLDAS
+        driver rewrites LAI = XLAIXY from the forcing file before every call)."""
+        self._check_rc(self._L.noahmp_b200_set_push(self._ctx, ",".join(fields).encode()))
+
+    def set_forcing_hints(self, hints):
+        """Bit-or of HINT_DZ8W_CONSTANT, HINT_VEGFRA_UNCHANGED, HINT_P8W_LEVELS_EQUAL: forcing planes the following
+        RESIDENT-mode calls need not upload again."""
+        self._check_rc(self._L.noahmp_b200_set_forcing_hints(self._ctx, int(hints)))
 
     def set_rebin(self, interval):
         """Re-bin land columns every `interval` RESIDENT-mode steps (0 = never)."""
@@ -223,6 +302,47 @@ class NoahMP:
         """CALL WTABLE_mmf_noahmp(...) on a tile that needs no halo (single tile = whole domain)."""
         a = _capi.make_wtable_args(self._hold(arrays), scalars)
         self._check_rc(self._L.noahmp_b200_wtable(self._ctx, C.byref(a)))
+
+    def wtable_device(self, arrays, scalars, stream=None):
+        """WTABLE_mmf_noahmp enqueued on `stream` (a cudaStream_t handle) behind the preceding step_device(): pass 1,
+        the NCCL halo exchange when a communicator is set, pass 2 and the column update; the host does not wait.
+        The marshalled argument list is cached per (arrays, scalars) pair."""
+        key = (id(arrays), id(scalars))
+        if getattr(self, "_wt_cache", (None,))[0] != key:
+            self._wt_cache = (key, _capi.make_wtable_args(self._hold(arrays), scalars), arrays)
+        self._check_rc(self._L.noahmp_b200_wtable_device(self._ctx, C.byref(self._wt_cache[1]), stream))
+
+    def wtable_exchange(self, stream=None):
+        self._check_rc(self._L.noahmp_b200_wtable_exchange(self._ctx, stream))
+
+    # ---- communicator of the tiles of one domain (NCCL inside the library) -----------------------------------
+    def comm_unique_id(self):
+        """128-byte NCCL id (numpy uint8) made by rank 0; the host program carries it to the other ranks."""
+        buf = np.zeros(128, np.uint8)
+        self._check_rc(self._L.noahmp_b200_comm_unique_id(buf.ctypes.data))
+        return buf
+
+    def comm_init(self, uid, rank, nranks):
+        uid = np.ascontiguousarray(uid, np.uint8)
+        assert uid.size == 128
+        self._check_rc(self._L.noahmp_b200_comm_init(self._ctx, uid.ctypes.data, int(rank), int(nranks)))
+
+    def comm_neighbours(self):
+        nb = (C.c_int * 4)()
+        self._check_rc(self._L.noahmp_b200_comm_neighbours(self._ctx, nb))
+        return tuple(nb)
+
+    # ---- global water / energy budget -------------------------------------------------------------------------
+    BUDGET_NAMES = ("storage_mm", "precip_mm", "et_mm", "runoff_mm", "erreng_wm2", "swe_mm", "columns", "steps")
+
+    def budget_enable(self, on=True):
+        self._check_rc(self._L.noahmp_b200_budget_enable(self._ctx, int(bool(on))))
+
+    def budget_read(self, global_sum=False, reset=False):
+        """dict of the eight fp64 sums (see include/noahmp_b200.h); global_sum: all-reduced over the communicator."""
+        out = (C.c_double * 8)()
+        self._check_rc(self._L.noahmp_b200_budget_read(self._ctx, out, int(bool(global_sum)), int(bool(reset))))
+        return dict(zip(self.BUDGET_NAMES, list(out)))
 
     def wtable_begin(self, arrays, scalars):
         a = _capi.make_wtable_args(self._hold(arrays), scalars)

@@ -142,6 +142,8 @@ def named_config(name):
         return Config("C2", 464, 224, dveg=4, water_frac=0.10)
     if name == "C3":
         return Config("C3", 4608, 3840, dveg=2, snow_frac=0.40, t_base=263.0, start=(2017, 1, 15, 0))
+    if name == "C5":  # the C3 grid with the Miguez-Macho & Fan groundwater scheme
+        return Config("C5", 4608, 3840, dveg=2, opt_run=5, snow_frac=0.40, t_base=263.0, start=(2017, 1, 15, 0))
     if name == "C4":
         return Config("C4", 7200, 3600, dveg=4, water_frac=0.69, glacier_frac=0.10, lat=(-60.0, 75.0),
                       lon=(-180.0, 180.0))
@@ -170,18 +172,19 @@ def clock(cfg, step):
     return y, julian, hour
 
 
-def tile_index(xp, cfg, xs, xe, ys, ye):
-    """int64 global column index g (0-based, i fastest) of the tile [xs..xe]x[ys..ye] (1-based incl)."""
+def tile_index(xp, cfg, xs, xe, ys, ye, jstride=1):
+    """int64 global column index g (0-based, i fastest) of the tile [xs..xe]x[ys..ye] (1-based incl); with
+    jstride > 1 only every jstride-th row of it (a row sample of the domain for the CPU arms of bench.py)."""
     ii = xp.arange(xe - xs + 1) + (xs - 1)
-    jj = xp.arange(ye - ys + 1) + (ys - 1)
+    jj = xp.arange((ye - ys) // jstride + 1) * jstride + (ys - 1)
     g = jj[:, None] * cfg.ni + ii[None, :]
     return g, ii, jj
 
 
-def static_fields(xp, cfg, xs=1, xe=None, ys=1, ye=None):
+def static_fields(xp, cfg, xs=1, xe=None, ys=1, ye=None, jstride=1):
     xe = xe or cfg.ni
     ye = ye or cfg.nj
-    g, ii, jj = tile_index(xp, cfg, xs, xe, ys, ye)
+    g, ii, jj = tile_index(xp, cfg, xs, xe, ys, ye, jstride)
     nj, ni = g.shape
     u = lambda f: uniform(xp, g, -1, f)
     water = u(F_WATER) < cfg.water_frac
