@@ -73,6 +73,18 @@ def load_json(*path):
         return None
 
 
+def kernel_constants(sunlit):
+    """Per-column DRAM bytes and executed warp-instructions of land_kernel<dynveg> from the committed ncu captures of a
+    night and a midday CONUS launch, interpolated linearly in the sunlit fraction of the timed steps."""
+    d = load_json("profiles", "r02_kernel_constants.json")
+    if not d:
+        return {}
+    n, m, cols = d["night"], d["midday"], float(d["columns"])
+    mix = lambda k: (n[k] + sunlit * (m[k] - n[k]))
+    return {"dram_bytes_per_column": mix("dram_bytes") / cols, "warp_instr_per_column": mix("warp_instr") / cols,
+            "simt_efficiency": mix("not_predicated_off_per_warp") / 32.0, "source": d["source"]}
+
+
 def load_peaks():
     d = load_json("MEASURED_PEAKS.json")
     if d and "hbm_gbs" in d:
@@ -312,11 +324,13 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     gpu_launches = model.launches - launches0
+    ev_day0 = torch.cuda.Event(enable_timing=True)
+    ev_day0.record(stream)
     for s in range(args.steps, nsteps):  # optional: one more whole day, outside the K timed steps
         device_step(k); k += 1
         ev[s + 1].record(stream)
     torch.cuda.synchronize()
-    step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(nsteps)]
+    step_ms = [(ev_day0 if s == args.steps else ev[s]).elapsed_time(ev[s + 1]) for s in range(nsteps)]
     total_ms = ev[0].elapsed_time(ev[args.steps])
     st1 = model.status()
     if st1.code:
@@ -378,13 +392,16 @@ def main():
             e2e_step(k); k += 1
         barrier()
         t0 = time.perf_counter()
+        e2e_calls = []
         for _ in range(args.steps):
+            t1 = time.perf_counter()
             stt = e2e_step(k); k += 1
+            e2e_calls.append(1e3 * (time.perf_counter() - t1))
         barrier()
         e2e_s = time.perf_counter() - t0
         if stt.code:
             raise SystemExit(f"e2e: model check failed code {stt.code}")
-        e2e = (e2e_s, h2d, d2h, nup)
+        e2e = (e2e_s, h2d, d2h, nup, e2e_calls)
         model.set_forcing_hints(0)
 
     # ---- e2e through the on-device forcing pipeline (row f2): forcing FILES every 3 h, interpolation on the GPU ------
@@ -455,7 +472,7 @@ def main():
         mean_ms = float(np.mean(step_ms[:args.steps]))
         alg_bytes = ALG_BYTES_PER_COLUMN_STEP + (ALG_BYTES_WTABLE if c5 else 0)
         achieved = alg_bytes * ncol / (mean_ms * 1e-3) / 1e9
-        kc = load_json("profiles", "r02_kernel_constants.json") or {}
+        kc = kernel_constants(sun_timed)
         peaks = load_json("profiles", "r01_peaks.json") or {}
         opc = load_json("profiles", "r02_opcount.json") or {}
         line = {
@@ -516,6 +533,7 @@ def main():
                                    f"{e2e[3]} forcing planes per call: DZ8W, VEGFRA and level 2 of P8W3D declared "
                                    "constant / unchanged / equal to level 1 with noahmp_b200_set_forcing_hints), pinned host buffers",
                            "ms_per_step": 1e3 * e2e_s_max / args.steps, "sunlit_fraction": sun_timed,
+                           "call_ms_rank0": [round(x, 2) for x in e2e[4]],
                            # the forcing upload is what bounds this call: bytes per rank / the box's pinned H2D rate
                            "pcie_floor_ms": e2e[1] / PCIE_H2D_GBPS / 1e6,
                            "pcie_note": f"{PCIE_H2D_GBPS} GB/s pinned H2D measured with tools/pcie_probe.py "

@@ -343,6 +343,7 @@ int noahmp_b200_comm_unique_id(void* id128);
 int noahmp_b200_comm_init(noahmp_b200_ctx* ctx, const void* id128, int rank, int nranks);
 /* ranks of the left, right, lower (smaller j) and upper neighbour tile, -1 at the domain edge */
 int noahmp_b200_comm_neighbours(const noahmp_b200_ctx* ctx, int neighbours[4]);
+void noahmp_b200_tile_neighbours(int nranks, int rank, int neighbours[4]);
 /* The halo exchange alone, between _begin and _end, on `stream` (cudaStream_t as void*, NULL = the context's). */
 int noahmp_b200_wtable_exchange(noahmp_b200_ctx* ctx, void* stream);
 /* noahmp_b200_wtable for a device-side stepping loop (RESIDENT mode): pass 1, halo, pass 2 and the column update are
@@ -418,6 +419,26 @@ typedef struct noahmp_init_args {
  * option in Noah-MP", :1171). */
 int noahmp_b200_init(noahmp_b200_ctx* ctx, const noahmp_init_args* args);
 unsigned long long noahmp_b200_sizeof_init_args(void);
+
+/* ---- one host process driving several GPUs ------------------------------------------------
+ * Replaces the IO-rank scatter / gather of the reference's MPI build (decompose_data_real/_int, write_io_real/_int,
+ * mpp/module_mpp_land.F90:645-857) by tile slicing: the process holds the whole-domain arrays, GPU r owns the tile
+ * mpp_land_partition_calc gives rank r, and every per-tile context copies its rows directly out of / into the global
+ * arrays.  The per-tile entry points accept this as well: memory bounds (ims:ime, jms:jme) may exceed the tile bounds. */
+typedef struct noahmp_b200_domain noahmp_b200_domain; /* opaque */
+noahmp_b200_domain* noahmp_b200_domain_create(const noahmp_tables* tables, int global_ni, int global_nj, int ntiles,
+                                              const int* devices /* [ntiles] CUDA device of each tile */);
+void noahmp_b200_domain_destroy(noahmp_b200_domain* d);
+int noahmp_b200_domain_ntiles(const noahmp_b200_domain* d);
+noahmp_b200_ctx* noahmp_b200_domain_tile(noahmp_b200_domain* d, int r);
+int noahmp_b200_domain_tile_bounds(const noahmp_b200_domain* d, int r, int* xstart, int* xend, int* ystart, int* yend);
+/* sync / math mode, fetch and push lists (NULL = leave), forcing hints of every tile */
+int noahmp_b200_domain_configure(noahmp_b200_domain* d, int sync_mode, int math_mode, const char* fetch, const char* push,
+                                 unsigned hints);
+/* CALL noahmplsm(...) with the GLOBAL arrays (memory bounds = the domain; the tile bounds of `args` are ignored): one
+ * worker thread per GPU runs its tile's call.  status = first failing column in the reference's loop order. */
+int noahmp_b200_domain_noahmplsm(noahmp_b200_domain* d, const noahmp_lsm_args* args, noahmp_status* status);
+int noahmp_b200_domain_sync_host(noahmp_b200_domain* d, const noahmp_lsm_args* args);
 
 /* ---- domain decomposition: replaces mpp_land_partition arithmetic ----------------------------
  * mpp/module_mpp_land.F90:124-141 (process grid), :245-288 (tile extents). All 1-based inclusive. */

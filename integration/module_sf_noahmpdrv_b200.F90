@@ -10,7 +10,12 @@ MODULE module_sf_noahmpdrv_b200
   USE, INTRINSIC :: ISO_C_BINDING
   IMPLICIT NONE
   PRIVATE
-  PUBLIC :: noahmplsm, noahmp_b200_start, noahmp_b200_stop, noahmp_b200_refresh_host
+  PUBLIC :: noahmplsm, NOAHMP_INIT, WTABLE_mmf_noahmp
+  PUBLIC :: noahmp_b200_start, noahmp_b200_start_parallel, noahmp_b200_stop, noahmp_b200_refresh_host
+  PUBLIC :: noahmp_b200_snapshot_begin, noahmp_b200_snapshot_wait, noahmp_b200_vegfra_changed
+  PUBLIC :: noahmp_b200_global_budget
+  PUBLIC :: noahmp_forcing_fields, noahmp_b200_forcing_static, noahmp_b200_forcing_upload, noahmp_b200_forcing_swap
+  PUBLIC :: noahmp_b200_forcing_apply, noahmplsm_device_forcing
 
   !> mirrors `noahmp_lsm_args` member for member
   TYPE, BIND(C) :: noahmp_lsm_args
@@ -179,6 +184,71 @@ MODULE module_sf_noahmpdrv_b200
     REAL(C_FLOAT)  :: value
   END TYPE noahmp_status
 
+  !> member for member include/noahmp_b200.h :: noahmp_wtable_args (the WTABLE_mmf_noahmp dummy list,
+  !> phys/module_sf_noahmp_groundwater.F90:14-22)
+  TYPE, BIND(C) :: noahmp_wtable_args
+    INTEGER(C_INT) :: nsoil
+    TYPE(C_PTR) :: xland
+    TYPE(C_PTR) :: xice
+    REAL(C_FLOAT) :: xice_threshold
+    INTEGER(C_INT) :: isice
+    TYPE(C_PTR) :: isltyp
+    TYPE(C_PTR) :: smoiseq
+    TYPE(C_PTR) :: dzs
+    REAL(C_FLOAT) :: wtddt
+    TYPE(C_PTR) :: fdepth
+    TYPE(C_PTR) :: area
+    TYPE(C_PTR) :: topo
+    INTEGER(C_INT) :: isurban
+    TYPE(C_PTR) :: ivgtyp
+    TYPE(C_PTR) :: rivercond
+    TYPE(C_PTR) :: riverbed
+    TYPE(C_PTR) :: eqwtd
+    TYPE(C_PTR) :: pexp
+    TYPE(C_PTR) :: smois
+    TYPE(C_PTR) :: sh2oxy
+    TYPE(C_PTR) :: smcwtd
+    TYPE(C_PTR) :: wtd
+    TYPE(C_PTR) :: qrf
+    TYPE(C_PTR) :: deeprech
+    TYPE(C_PTR) :: qspring
+    TYPE(C_PTR) :: qslat
+    TYPE(C_PTR) :: qrfs
+    TYPE(C_PTR) :: qsprings
+    TYPE(C_PTR) :: rech
+    INTEGER(C_INT) :: ids
+    INTEGER(C_INT) :: ide
+    INTEGER(C_INT) :: jds
+    INTEGER(C_INT) :: jde
+    INTEGER(C_INT) :: kds
+    INTEGER(C_INT) :: kde
+    INTEGER(C_INT) :: ims
+    INTEGER(C_INT) :: ime
+    INTEGER(C_INT) :: jms
+    INTEGER(C_INT) :: jme
+    INTEGER(C_INT) :: kms
+    INTEGER(C_INT) :: kme
+    INTEGER(C_INT) :: its
+    INTEGER(C_INT) :: ite
+    INTEGER(C_INT) :: jts
+    INTEGER(C_INT) :: jte
+    INTEGER(C_INT) :: kts
+    INTEGER(C_INT) :: kte
+  END TYPE noahmp_wtable_args
+
+  !> one forcing file for the on-device forcing pipeline (include/noahmp_b200.h :: noahmp_forcing_fields)
+  TYPE, BIND(C) :: noahmp_forcing_fields
+    TYPE(C_PTR) :: t
+    TYPE(C_PTR) :: q
+    TYPE(C_PTR) :: u
+    TYPE(C_PTR) :: v
+    TYPE(C_PTR) :: p
+    TYPE(C_PTR) :: lw
+    TYPE(C_PTR) :: sw
+    TYPE(C_PTR) :: pcp
+    TYPE(C_PTR) :: fpar
+  END TYPE noahmp_forcing_fields
+
   !> member for member include/noahmp_b200.h :: noahmp_init_args (the NOAHMP_INIT dummy list)
   TYPE, BIND(C) :: noahmp_init_args
     TYPE(C_PTR) :: snow
@@ -275,11 +345,16 @@ MODULE module_sf_noahmpdrv_b200
   END TYPE noahmp_init_args
 
   INTEGER(C_INT), PARAMETER :: NOAHMP_SYNC_FULL = 0, NOAHMP_SYNC_RESIDENT = 1
+  INTEGER(C_INT), PARAMETER :: NOAHMP_HINT_DZ8W_CONSTANT = 1, NOAHMP_HINT_VEGFRA_UNCHANGED = 2, &
+                               NOAHMP_HINT_P8W_LEVELS_EQUAL = 4
   INTEGER, PARAMETER :: NOAHMP_TABLES_BYTES = 12712   ! sizeof(noahmp_tables); checked at start-up
 
   TYPE(C_PTR), SAVE :: ctx = C_NULL_PTR
   INTEGER(C_INT8_T), SAVE, TARGET :: tables(NOAHMP_TABLES_BYTES)
   TYPE(noahmp_lsm_args), SAVE :: last_args
+  INTEGER, SAVE :: global_nx = 0, global_ny = 0      ! extents of the whole domain when the run is tiled over GPUs
+  INTEGER(C_INT), SAVE :: hints = 0
+  LOGICAL, SAVE :: vegfra_new = .TRUE.
 
   INTERFACE
     FUNCTION noahmp_b200_read_tables(dir, dataset, soil, tbl) BIND(C, NAME="noahmp_b200_read_tables") RESULT(rc)
@@ -318,6 +393,64 @@ MODULE module_sf_noahmpdrv_b200
     FUNCTION noahmp_b200_output_wait(c) BIND(C, NAME="noahmp_b200_output_wait") RESULT(rc)
       IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION noahmp_b200_set_push(c, fields) BIND(C, NAME="noahmp_b200_set_push") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; CHARACTER(KIND=C_CHAR), INTENT(IN) :: fields(*); INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_set_forcing_hints(c, h) BIND(C, NAME="noahmp_b200_set_forcing_hints") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT), VALUE :: h; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_get_status(c, st) BIND(C, NAME="noahmp_b200_get_status") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_status) :: st; INTEGER(C_INT) :: rc
+    END FUNCTION
+    ! ---- opt_run = 5 groundwater and the communicator of the tiles
+    FUNCTION noahmp_b200_wtable(c, args) BIND(C, NAME="noahmp_b200_wtable") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_wtable_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_wtable_begin(c, args) BIND(C, NAME="noahmp_b200_wtable_begin") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_wtable_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_wtable_exchange(c, stream) BIND(C, NAME="noahmp_b200_wtable_exchange") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c, stream; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_wtable_end(c, args) BIND(C, NAME="noahmp_b200_wtable_end") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_wtable_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_wtable_sync_host(c, args) BIND(C, NAME="noahmp_b200_wtable_sync_host") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_wtable_args), INTENT(IN) :: args; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_comm_unique_id(id) BIND(C, NAME="noahmp_b200_comm_unique_id") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: id; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_comm_init(c, id, rank, nranks) BIND(C, NAME="noahmp_b200_comm_init") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c, id; INTEGER(C_INT), VALUE :: rank, nranks; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_budget_enable(c, enable) BIND(C, NAME="noahmp_b200_budget_enable") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT), VALUE :: enable; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION noahmp_b200_budget_read(c, out8, global, reset) BIND(C, NAME="noahmp_b200_budget_read") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; REAL(C_DOUBLE) :: out8(8); INTEGER(C_INT), VALUE :: global, reset
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    ! ---- forcing pipeline on the device (row f2)
+    FUNCTION c_forcing_static(c, lat2d, lon2d, zlvl) BIND(C, NAME="noahmp_b200_forcing_static") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c, lat2d, lon2d; REAL(C_FLOAT), VALUE :: zlvl; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION c_forcing_upload(c, slot, f) BIND(C, NAME="noahmp_b200_forcing_upload") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT), VALUE :: slot; TYPE(noahmp_forcing_fields), INTENT(IN) :: f
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION c_forcing_swap(c) BIND(C, NAME="noahmp_b200_forcing_swap") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION c_forcing_apply(c, fraction, iday, ihour, iminute, isecond, dt, julian) &
+        BIND(C, NAME="noahmp_b200_forcing_apply") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; REAL(C_FLOAT), VALUE :: fraction, dt
+      INTEGER(C_INT), VALUE :: iday, ihour, iminute, isecond; REAL(C_FLOAT) :: julian; INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION c_noahmplsm_device_forcing(c, args, st) BIND(C, NAME="noahmp_b200_noahmplsm_device_forcing") RESULT(rc)
+      IMPORT; TYPE(C_PTR), VALUE :: c; TYPE(noahmp_lsm_args), INTENT(IN) :: args; TYPE(noahmp_status) :: st
+      INTEGER(C_INT) :: rc
+    END FUNCTION
   END INTERFACE
 
 CONTAINS
@@ -336,8 +469,44 @@ CONTAINS
     IF (resident) THEN
       rc = noahmp_b200_set_mode(ctx, NOAHMP_SYNC_RESIDENT)
       rc = noahmp_b200_set_fetch(ctx, "tslb,xlaixy"//C_NULL_CHAR)   ! what land_driver_exe prints every step (:567-572)
+      ! READFORC_HRLDAS overwrites LAI (= XLAIXY) from the forcing file before every call (:335, :403)
+      rc = noahmp_b200_set_push(ctx, "xlaixy"//C_NULL_CHAR)
+      ! DZ8W = 2*zlvl never changes (:344); P8W(:,2,:) = P8W(:,1,:) (:338); VEGFRA changes only when a forcing file
+      ! brought a new one: the driver says so with noahmp_b200_vegfra_changed()
+      hints = IOR(NOAHMP_HINT_DZ8W_CONSTANT, NOAHMP_HINT_P8W_LEVELS_EQUAL)
+      rc = noahmp_b200_set_forcing_hints(ctx, hints)
     END IF
   END SUBROUTINE noahmp_b200_start
+
+  !> Tiled run, one MPI rank per GPU: after noahmp_b200_start.  `id128` is the 128-byte NCCL id rank 0 obtained from
+  !> noahmp_b200_comm_unique_id and the driver broadcast (MPI_Bcast(id128, 128, MPI_BYTE, 0, comm)); nx_global / ny_global
+  !> are the extents of the whole domain.  From here on WTABLE_mmf_noahmp exchanges its halo over NCCL and
+  !> noahmp_b200_global_budget sums over all tiles.
+  SUBROUTINE noahmp_b200_start_parallel(id128, rank, nranks, nx_global, ny_global)
+    INTEGER(C_INT8_T), INTENT(IN), TARGET :: id128(128)
+    INTEGER, INTENT(IN) :: rank, nranks, nx_global, ny_global
+    INTEGER(C_INT) :: rc
+    rc = noahmp_b200_comm_init(ctx, C_LOC(id128), INT(rank, C_INT), INT(nranks, C_INT))
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: NCCL communicator could not be created")
+    global_nx = nx_global
+    global_ny = ny_global
+    rc = noahmp_b200_budget_enable(ctx, 1_C_INT)
+  END SUBROUTINE noahmp_b200_start_parallel
+
+  !> call after READFORC_HRLDAS delivered a VEGFRA that differs from the previous one
+  SUBROUTINE noahmp_b200_vegfra_changed()
+    vegfra_new = .TRUE.
+  END SUBROUTINE noahmp_b200_vegfra_changed
+
+  !> eight fp64 sums over all tiles (one ncclAllReduce): storage, precipitation, ET, runoff (mm), energy residual
+  !> (W/m2), SWE (mm), columns, steps — see include/noahmp_b200.h; reset starts a new reporting interval
+  SUBROUTINE noahmp_b200_global_budget(sums, reset)
+    REAL(C_DOUBLE), INTENT(OUT) :: sums(8)
+    LOGICAL, INTENT(IN) :: reset
+    INTEGER(C_INT) :: rc
+    rc = noahmp_b200_budget_read(ctx, sums, 1_C_INT, MERGE(1_C_INT, 0_C_INT, reset))
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: budget_read failed (call noahmp_b200_start_parallel first)")
+  END SUBROUTINE noahmp_b200_global_budget
 
   !> RESIDENT mode: call before hrldas_output / restart writes (driver :440-592) to refresh every host array
   SUBROUTINE noahmp_b200_refresh_host()
@@ -705,6 +874,10 @@ CONTAINS
     a%kts = KTS
     a%kte = KTE
     last_args = a
+    IF (hints /= 0) THEN
+      rc = noahmp_b200_set_forcing_hints(ctx, MERGE(hints, IOR(hints, NOAHMP_HINT_VEGFRA_UNCHANGED), vegfra_new))
+      vegfra_new = .FALSE.
+    END IF
     rc = noahmp_b200_noahmplsm(ctx, a, st)
     IF (rc /= 0) THEN
       ! same fatal convention as the reference (util/module_wrf_utilities.F:12-24), same message texts
@@ -857,5 +1030,137 @@ CONTAINS
     IF (rc /= 0 .AND. iopt_run == 5) CALL wrf_error_fatal('Not enough fields to use groundwater option in Noah-MP')
     IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200_init failed")
   END SUBROUTINE NOAHMP_INIT
+
+  !> Drop-in for WTABLE_mmf_noahmp (phys/module_sf_noahmp_groundwater.F90:14-22; call site
+  !> driver/module_hrldas_noahmp_driver.F90:420-436): same name, dummy list and order.  In a tiled run the reference's
+  !> MPI build passes ids = its ... and never exchanges a halo, so its answer depends on the rank count; here the domain
+  !> extents given to noahmp_b200_start_parallel replace ids..jde and the library exchanges the KCELL / HEAD halo over
+  !> NCCL inside the call: every tiling reproduces the sequential single-domain result.
+  SUBROUTINE WTABLE_mmf_noahmp( &
+      NSOIL, XLAND, XICE, XICE_THRESHOLD, ISICE, ISLTYP, SMOISEQ, DZS, WTDDT, FDEPTH, AREA, TOPO, ISURBAN, IVGTYP, &
+      RIVERCOND, RIVERBED, EQWTD, PEXP, SMOIS, SH2OXY, SMCWTD, WTD, QRF, DEEPRECH, QSPRING, QSLAT, QRFS, QSPRINGS, &
+      RECH, IDS, IDE, JDS, JDE, KDS, KDE, IMS, IME, JMS, JME, KMS, KME, ITS, ITE, JTS, JTE, KTS, KTE)
+    IMPLICIT NONE
+    INTEGER, INTENT(IN) :: IDS, IDE, JDS, JDE, KDS, KDE, IMS, IME, JMS, JME, KMS, KME, ITS, ITE, JTS, JTE, KTS, KTE
+    REAL, INTENT(IN) :: WTDDT
+    REAL, INTENT(IN) :: XICE_THRESHOLD
+    INTEGER, INTENT(IN) :: ISICE
+    REAL, DIMENSION(ims:ime, jms:jme), INTENT(IN), TARGET :: XLAND, XICE
+    INTEGER, DIMENSION(ims:ime, jms:jme), INTENT(IN), TARGET :: ISLTYP, IVGTYP
+    INTEGER, INTENT(IN) :: NSOIL
+    INTEGER, INTENT(IN) :: ISURBAN
+    REAL, DIMENSION(ims:ime, 1:nsoil, jms:jme), INTENT(IN), TARGET :: SMOISEQ
+    REAL, DIMENSION(1:nsoil), INTENT(IN), TARGET :: DZS
+    REAL, DIMENSION(ims:ime, jms:jme), INTENT(IN), TARGET :: FDEPTH, AREA, TOPO, EQWTD, PEXP, RIVERBED, RIVERCOND
+    REAL, DIMENSION(ims:ime, 1:nsoil, jms:jme), INTENT(INOUT), TARGET :: SMOIS, SH2OXY
+    REAL, DIMENSION(ims:ime, jms:jme), INTENT(INOUT), TARGET :: WTD, SMCWTD, DEEPRECH, QSLAT, QRFS, QSPRINGS, RECH
+    REAL, DIMENSION(ims:ime, jms:jme), INTENT(OUT), TARGET :: QRF, QSPRING
+    TYPE(noahmp_wtable_args) :: a
+    INTEGER(C_INT) :: rc
+
+    a%nsoil = NSOIL
+    a%xland = C_LOC(XLAND)
+    a%xice = C_LOC(XICE)
+    a%xice_threshold = XICE_THRESHOLD
+    a%isice = ISICE
+    a%isltyp = C_LOC(ISLTYP)
+    a%smoiseq = C_LOC(SMOISEQ)
+    a%dzs = C_LOC(DZS)
+    a%wtddt = WTDDT
+    a%fdepth = C_LOC(FDEPTH)
+    a%area = C_LOC(AREA)
+    a%topo = C_LOC(TOPO)
+    a%isurban = ISURBAN
+    a%ivgtyp = C_LOC(IVGTYP)
+    a%rivercond = C_LOC(RIVERCOND)
+    a%riverbed = C_LOC(RIVERBED)
+    a%eqwtd = C_LOC(EQWTD)
+    a%pexp = C_LOC(PEXP)
+    a%smois = C_LOC(SMOIS)
+    a%sh2oxy = C_LOC(SH2OXY)
+    a%smcwtd = C_LOC(SMCWTD)
+    a%wtd = C_LOC(WTD)
+    a%qrf = C_LOC(QRF)
+    a%deeprech = C_LOC(DEEPRECH)
+    a%qspring = C_LOC(QSPRING)
+    a%qslat = C_LOC(QSLAT)
+    a%qrfs = C_LOC(QRFS)
+    a%qsprings = C_LOC(QSPRINGS)
+    a%rech = C_LOC(RECH)
+    a%ids = IDS
+    a%ide = IDE
+    a%jds = JDS
+    a%jde = JDE
+    a%kds = KDS
+    a%kde = KDE
+    a%ims = IMS
+    a%ime = IME
+    a%jms = JMS
+    a%jme = JME
+    a%kms = KMS
+    a%kme = KME
+    a%its = ITS
+    a%ite = ITE
+    a%jts = JTS
+    a%jte = JTE
+    a%kts = KTS
+    a%kte = KTE
+    IF (global_nx > 0) THEN   ! tiled run: the stencil and its clipping refer to the whole domain
+      a%ids = 1
+      a%ide = global_nx
+      a%jds = 1
+      a%jde = global_ny
+    END IF
+    rc = noahmp_b200_wtable(ctx, a)
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200_wtable failed")
+  END SUBROUTINE WTABLE_mmf_noahmp
+
+  ! ---- forcing pipeline on the device (INTEGRATION.md section 4) ---------------------------------------------------
+  SUBROUTINE noahmp_b200_forcing_static(lat2d, lon2d, zlvl)
+    REAL, INTENT(IN), TARGET, CONTIGUOUS :: lat2d(:,:), lon2d(:,:)
+    REAL, INTENT(IN) :: zlvl
+    INTEGER(C_INT) :: rc
+    rc = c_forcing_static(ctx, C_LOC(lat2d), C_LOC(lon2d), REAL(zlvl, C_FLOAT))
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200_forcing_static failed")
+  END SUBROUTINE noahmp_b200_forcing_static
+
+  SUBROUTINE noahmp_b200_forcing_upload(slot, f)
+    INTEGER, INTENT(IN) :: slot
+    TYPE(noahmp_forcing_fields), INTENT(IN) :: f
+    INTEGER(C_INT) :: rc
+    rc = c_forcing_upload(ctx, INT(slot, C_INT), f)
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200_forcing_upload failed")
+  END SUBROUTINE noahmp_b200_forcing_upload
+
+  SUBROUTINE noahmp_b200_forcing_swap()
+    INTEGER(C_INT) :: rc
+    rc = c_forcing_swap(ctx)
+  END SUBROUTINE noahmp_b200_forcing_swap
+
+  SUBROUTINE noahmp_b200_forcing_apply(fraction, iday, ihour, iminute, isecond, dt, julian)
+    REAL, INTENT(IN) :: fraction, dt
+    INTEGER, INTENT(IN) :: iday, ihour, iminute, isecond
+    REAL, INTENT(OUT) :: julian
+    REAL(C_FLOAT) :: j
+    INTEGER(C_INT) :: rc
+    rc = c_forcing_apply(ctx, REAL(fraction, C_FLOAT), INT(iday, C_INT), INT(ihour, C_INT), INT(iminute, C_INT), &
+                         INT(isecond, C_INT), REAL(dt, C_FLOAT), j)
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200_forcing_apply failed")
+    julian = j
+  END SUBROUTINE noahmp_b200_forcing_apply
+
+  !> the step with the forcing planes noahmp_b200_forcing_apply filled: call noahmplsm once (it records its argument
+  !> list), then this routine for the following steps
+  SUBROUTINE noahmplsm_device_forcing(itimestep, yr, julian)
+    INTEGER, INTENT(IN) :: itimestep, yr
+    REAL, INTENT(IN) :: julian
+    TYPE(noahmp_status) :: st
+    INTEGER(C_INT) :: rc
+    last_args%itimestep = itimestep
+    last_args%yr = yr
+    last_args%julian = julian
+    rc = c_noahmplsm_device_forcing(ctx, last_args, st)
+    IF (rc /= 0) CALL wrf_error_fatal("noahmp_b200: model check failed in noahmplsm_device_forcing")
+  END SUBROUTINE noahmplsm_device_forcing
 
 END MODULE module_sf_noahmpdrv_b200

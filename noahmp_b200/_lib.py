@@ -75,8 +75,17 @@ SYMBOLS = {
     "noahmp_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "noahmp_b200_comm_init": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int]),
     "noahmp_b200_comm_neighbours": (C.c_int, [_ctx, C.POINTER(C.c_int)]),
+    "noahmp_b200_tile_neighbours": (None, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "noahmp_b200_budget_enable": (C.c_int, [_ctx, C.c_int]),
     "noahmp_b200_budget_read": (C.c_int, [_ctx, C.POINTER(C.c_double), C.c_int, C.c_int]),
+    "noahmp_b200_domain_create": (C.c_void_p, [_pt, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "noahmp_b200_domain_destroy": (None, [C.c_void_p]),
+    "noahmp_b200_domain_ntiles": (C.c_int, [C.c_void_p]),
+    "noahmp_b200_domain_tile": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "noahmp_b200_domain_tile_bounds": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4),
+    "noahmp_b200_domain_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_uint]),
+    "noahmp_b200_domain_noahmplsm": (C.c_int, [C.c_void_p, _pa, _ps]),
+    "noahmp_b200_domain_sync_host": (C.c_int, [C.c_void_p, _pa]),
     "noahmp_b200_proc_grid": (None, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "noahmp_b200_tile": (None, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
 }

@@ -54,8 +54,11 @@ NMP_DEV float DESAT_I(float T) {
 NMP_DEV void ESAT(float T, float& ESW, float& ESI, float& DESW, float& DESI) {
   ESW = ESAT_W(T); ESI = ESAT_I(T); DESW = DESAT_W(T); DESI = DESAT_I(T);
 }
+// NMP_ESAT_SEL=1 skips the unused pair behind warp votes: measured SLOWER (2.333 vs 2.248 ms per 4.4 M columns over a
+// diurnal cycle, profiles/r02_notes.md) — the kernel is latency-bound and the four independent Horner chains overlap
+// for free, while the votes and branches add to the dependent path.  Default: evaluate and select.
 #ifndef NMP_ESAT_SEL
-#define NMP_ESAT_SEL 1
+#define NMP_ESAT_SEL 0
 #endif
 // ES = (T > 0) ? ESATW : ESATI and the matching derivative
 NMP_DEV void ESAT_SEL(float T, float& ES, float& DES) {

@@ -190,6 +190,9 @@ __global__ void init_groundwater_kernel(const nmpf::InitParams P) {
   if (il >= P.itf_n || jl >= P.jtf_n) return;
   const int I = P.its + il, J = P.jts + jl;
   const int ISLTYP = __float_as_int(P.f[nmpf::IF_isltyp][c]), IVGTYP = __float_as_int(P.f[nmpf::IF_ivgtyp][c]);
+  // a missing-field fill (e.g. -9999) was flagged by init_cell_kernel (err = 1, "lsminit: out of range value of
+  // ISLTYP"); it must not index the soil tables here
+  if (ISLTYP < 1 || ISLTYP > NOAHMP_NSLTYPE) return;
   const bool land = IVGTYP != P.iswater && IVGTYP != P.isice;
   const float area = P.f[nmpf::IF_areaxy][c];
   float WTD = P.f[nmpf::IF_zwtxy][c];

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -71,6 +72,11 @@ struct PlaneDesc {
 
 struct noahmp_b200_ctx {
   int device = 0, ni = 0, nj = 0;
+  // Layout of the caller's host arrays in the current call: memory extent mi x mj (ims:ime, jms:jme) and the offset
+  // (x0, y0) of this context's tile (its:ite, jts:jte) inside it.  HRLDAS allocates exactly the tile (mi = ni, x0 = 0);
+  // a single host process that holds the whole domain and drives one context per GPU passes the same global arrays to
+  // every context with different tile bounds (row f4: tile slicing instead of the IO-rank scatter / gather).
+  int h_mi = 0, h_mj = 0, h_x0 = 0, h_y0 = 0, h_its = 1, h_jts = 1;
   NmpComm comm;                            // NCCL communicator of the tiles of one domain (optional)
   double* d_budget = nullptr;              // NBUDGET running sums (noahmp_b200_budget_*)
   bool budget_on = false;
@@ -277,7 +283,7 @@ static void pin(noahmp_b200_ctx* ctx, const void* p, size_t bytes) {
       unpin_one(ctx, e.second);
     }
   }
-  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);  // contexts on other GPUs may share the array
   if (e == cudaSuccess) { ctx->registered[p] = bytes; ctx->pinned_bytes += bytes; }
   else {
     cudaGetLastError();         // already pinned by the caller, or not pinnable: plain pageable copy
@@ -293,10 +299,11 @@ static void unpin_all(noahmp_b200_ctx* ctx) {
   ctx->pinned_bytes = 0;
 }
 
-static int check_bounds(const noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
-  // HRLDAS allocates exactly the tile: ims=its ... (driver/module_hrldas_noahmp_driver.F90:112-129)
-  if (a->ims != a->its || a->ime != a->ite || a->jms != a->jts || a->jme != a->jte) {
-    set_error("memory bounds must equal tile bounds (ims=its, ime=ite, jms=jts, jme=jte) as in HRLDAS");
+static int check_bounds(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
+  // HRLDAS allocates exactly the tile: ims=its ... (driver/module_hrldas_noahmp_driver.F90:112-129); memory bounds that
+  // CONTAIN the tile are accepted too (WRF-style halos; one host process holding the whole domain)
+  if (a->ims > a->its || a->ime < a->ite || a->jms > a->jts || a->jme < a->jte) {
+    set_error("memory bounds must contain the tile bounds (ims<=its, ime>=ite, jms<=jts, jme>=jte)");
     return NOAHMP_ERR_ARG;
   }
   if (a->ite - a->its + 1 != ctx->ni || a->jte - a->jts + 1 != ctx->nj) {
@@ -308,7 +315,36 @@ static int check_bounds(const noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
     set_error("vertical bounds must contain levels 1 and 2 with kts=1");
     return NOAHMP_ERR_ARG;
   }
+  ctx->h_mi = a->ime - a->ims + 1;
+  ctx->h_mj = a->jme - a->jms + 1;
+  ctx->h_x0 = a->its - a->ims;
+  ctx->h_y0 = a->jts - a->jms;
+  ctx->h_its = a->its;
+  ctx->h_jts = a->jts;
   return 0;
+}
+
+// Copy rows [j0, j1) of a tile-shaped device array (ni x layers x nj, Fortran (i,k,j) order) from / to the caller's
+// array of the same field, whose memory extent may exceed the tile (h_mi, h_x0, h_y0).  One contiguous copy when the
+// memory is the tile, else a pitched copy of (j1-j0)*layers rows of ni words.
+static cudaError_t copy_field_rows(const noahmp_b200_ctx* ctx, float* dev, float* host, int layers, int j0, int j1,
+                                   bool to_device, cudaStream_t st) {
+  const size_t ni = ctx->ni, mi = ctx->h_mi, L = layers;
+  float* h = host + (size_t)ctx->h_x0 + ((size_t)(ctx->h_y0 + j0) * L) * mi;
+  float* d = dev + (size_t)j0 * L * ni;
+  const size_t rows = (size_t)(j1 - j0) * L;
+  if (rows == 0) return cudaSuccess;
+  if (mi == ni)
+    return to_device ? cudaMemcpyAsync(d, h, sizeof(float) * ni * rows, cudaMemcpyHostToDevice, st)
+                     : cudaMemcpyAsync(h, d, sizeof(float) * ni * rows, cudaMemcpyDeviceToHost, st);
+  return to_device ? cudaMemcpy2DAsync(d, sizeof(float) * ni, h, sizeof(float) * mi, sizeof(float) * ni, rows,
+                                       cudaMemcpyHostToDevice, st)
+                   : cudaMemcpy2DAsync(h, sizeof(float) * mi, d, sizeof(float) * ni, sizeof(float) * ni, rows,
+                                       cudaMemcpyDeviceToHost, st);
+}
+// bytes of the caller's whole array of a field with `layers` layers (what gets page-locked)
+static size_t host_bytes(const noahmp_b200_ctx* ctx, int layers) {
+  return sizeof(float) * (size_t)ctx->h_mi * (size_t)ctx->h_mj * (size_t)layers;
 }
 
 static void fill_scalars(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
@@ -379,18 +415,22 @@ static int build_plane_descs(noahmp_b200_ctx* ctx) {
   return 0;
 }
 
-// H2D of one 2-D plane; for 3-D atmospheric arrays (i,k,j) picks level `lev` (1-based)
-static int h2d_plane(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, int kms, int lev) {
-  const size_t ni = ctx->ni, nj = ctx->nj;
+// H2D of rows [j0, j1) of one 2-D plane; for 3-D atmospheric arrays (i,k,j) picks level `lev` (1-based)
+static int h2d_rows(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, int kms, int lev, int j0, int j1,
+                    cudaStream_t st) {
   if (nk == 1) {
-    pin(ctx, src, sizeof(float) * ni * nj);
-    CK(cudaMemcpyAsync(dst, src, sizeof(float) * ni * nj, cudaMemcpyHostToDevice, ctx->stream));
+    CK(copy_field_rows(ctx, dst, const_cast<float*>(src), 1, j0, j1, true, st));
   } else {
-    pin(ctx, src, sizeof(float) * ni * nj * nk);
-    CK(cudaMemcpy2DAsync(dst, sizeof(float) * ni, src + (size_t)(lev - kms) * ni, sizeof(float) * ni * nk,
-                         sizeof(float) * ni, nj, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t ni = ctx->ni, mi = ctx->h_mi;
+    const float* h = src + (size_t)ctx->h_x0 + ((size_t)(ctx->h_y0 + j0) * nk + (size_t)(lev - kms)) * mi;
+    CK(cudaMemcpy2DAsync(dst + (size_t)j0 * ni, sizeof(float) * ni, h, sizeof(float) * mi * nk, sizeof(float) * ni, j1 - j0,
+                         cudaMemcpyHostToDevice, st));
   }
   return 0;
+}
+static int h2d_plane(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, int kms, int lev) {
+  pin(ctx, src, host_bytes(ctx, nk));
+  return h2d_rows(ctx, dst, src, nk, kms, lev, 0, ctx->nj, ctx->stream);
 }
 
 static int upload_forcing(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
@@ -508,9 +548,8 @@ static int upload_state(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, bool all
     if (!want) continue;
     const float* src = host_ptr(a, f);
     if (!src) { set_error(std::string("null array: ") + kFields[f].name); return NOAHMP_ERR_ARG; }
-    const size_t bytes = sizeof(float) * ctx->ncell * kFields[f].layers;
-    pin(ctx, src, bytes);
-    CK(cudaMemcpyAsync(ctx->d_grid[f], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    pin(ctx, src, host_bytes(ctx, kFields[f].layers));
+    CK(copy_field_rows(ctx, ctx->d_grid[f], const_cast<float*>(src), kFields[f].layers, 0, ctx->nj, true, ctx->stream));
     ctx->grid_init[f] = true;
   }
   return 0;
@@ -520,9 +559,8 @@ static int download_state(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a) {
   for (int f = 0; f < NFIELDS; ++f) {
     if (f == F_smoiseq) continue;  // INTENT(IN) in effect: never written by noahmplsm
     float* dst = host_ptr(a, f);
-    const size_t bytes = sizeof(float) * ctx->ncell * kFields[f].layers;
-    pin(ctx, dst, bytes);
-    CK(cudaMemcpyAsync(dst, ctx->d_grid[f], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    pin(ctx, dst, host_bytes(ctx, kFields[f].layers));
+    CK(copy_field_rows(ctx, ctx->d_grid[f], dst, kFields[f].layers, 0, ctx->nj, false, ctx->stream));
   }
   return 0;
 }
@@ -536,8 +574,8 @@ static void decode_status(noahmp_b200_ctx* ctx, noahmp_status* st) {
     st->code = (int)((key >> 32) & 0x7f);
     unsigned vb = (unsigned)(key & 0xffffffffu);
     memcpy(&st->value, &vb, 4);
-    st->i = (int)(cell % (unsigned)ctx->ni) + 1;
-    st->j = (int)(cell / (unsigned)ctx->ni) + 1;
+    st->i = (int)(cell % (unsigned)ctx->ni) + ctx->h_its;  // Fortran (i,j) in the caller's index space
+    st->j = (int)(cell / (unsigned)ctx->ni) + ctx->h_jts;
   }
 }
 
@@ -972,19 +1010,6 @@ static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
   return 0;
 }
 
-// H2D of rows [j0, j1) of one forcing plane
-static int h2d_rows(noahmp_b200_ctx* ctx, float* dst, const float* src, int nk, int kms, int lev, int j0, int j1,
-                    cudaStream_t st) {
-  const size_t ni = ctx->ni;
-  if (nk == 1) {
-    CK(cudaMemcpyAsync(dst + (size_t)j0 * ni, src + (size_t)j0 * ni, sizeof(float) * ni * (j1 - j0), cudaMemcpyHostToDevice, st));
-  } else {
-    CK(cudaMemcpy2DAsync(dst + (size_t)j0 * ni, sizeof(float) * ni, src + (size_t)j0 * ni * nk + (size_t)(lev - kms) * ni,
-                         sizeof(float) * ni * nk, sizeof(float) * ni, j1 - j0, cudaMemcpyHostToDevice, st));
-  }
-  return 0;
-}
-
 // gather of compact range [first, first+count) of one field (all its layers) from the grid-order staging
 __global__ void gather_range_kernel(const PlaneDesc* __restrict__ planes, const int* __restrict__ cell, float* state,
                                     long long np, int ni, long long first, long long count) {
@@ -1001,7 +1026,7 @@ __global__ void gather_range_kernel(const PlaneDesc* __restrict__ planes, const 
 // their way up and the requested result fields of chunk c-1 on their way down (three streams, events in between).
 // Columns of a class are stored in grid order, so a row chunk is one contiguous compact range per class.
 static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, int nchunks, bool upload = true) {
-  const int nk = a->kme - a->kms + 1, kms = a->kms, ni = ctx->ni, nj = ctx->nj;
+  const int nk = a->kme - a->kms + 1, kms = a->kms;
   const auto t_begin = std::chrono::steady_clock::now();
   if (!ctx->s_in) {
     CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -1039,12 +1064,12 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
       if (pl.id == FC_P2 && (ctx->hints & NOAHMP_HINT_P8W_LEVELS_EQUAL)) skip = true;
       if (!skip) planes[nplanes++] = pl;
     }
-    for (int k = 0; k < nplanes; ++k) pin(ctx, planes[k].src, sizeof(float) * (size_t)ni * nj * planes[k].nk);
+    for (int k = 0; k < nplanes; ++k) pin(ctx, planes[k].src, host_bytes(ctx, planes[k].nk));
   }
-  for (int f : ctx->fetch) pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
+  for (int f : ctx->fetch) pin(ctx, host_ptr(a, f), host_bytes(ctx, kFields[f].layers));
   for (int f : ctx->push) {
     if (!host_ptr(a, f)) { set_error(std::string("null array in the push list: ") + kFields[f].name); return NOAHMP_ERR_ARG; }
-    pin(ctx, host_ptr(a, f), sizeof(float) * ctx->ncell * kFields[f].layers);
+    pin(ctx, host_ptr(a, f), host_bytes(ctx, kFields[f].layers));
   }
 
   // host forcing supersedes device pointers bound earlier with bind_forcing()
@@ -1114,8 +1139,7 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
     // INOUT arrays the driver rewrites before every call (e.g. XLAIXY from the forcing file): rows up, then into
     // the compact planes of this chunk's columns
     for (int f : ctx->push) {
-      const size_t L = kFields[f].layers, off = (size_t)j0 * ni * L, cnt = (size_t)(j1 - j0) * ni * L;
-      CK(cudaMemcpyAsync(ctx->d_grid[f] + off, host_ptr(a, f) + off, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->s_in));
+      CK(copy_field_rows(ctx, ctx->d_grid[f], host_ptr(a, f), kFields[f].layers, j0, j1, true, ctx->s_in));
       waited = true;
     }
     if (waited) {
@@ -1152,9 +1176,7 @@ static int step_resident_pipelined(noahmp_b200_ctx* ctx, const noahmp_lsm_args* 
       CK(cudaEventRecord(ctx->ev_k[c], sk));
       CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
       for (int f : ctx->fetch) {
-        const size_t L = kFields[f].layers, off = (size_t)j0 * ni * L, cnt = (size_t)(j1 - j0) * ni * L;
-        CK(cudaMemcpyAsync(host_ptr(a, f) + off, ctx->d_grid[f] + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost,
-                           ctx->s_out));
+        CK(copy_field_rows(ctx, ctx->d_grid[f], host_ptr(a, f), kFields[f].layers, j0, j1, false, ctx->s_out));
       }
       if (ctx->trace) CK(cudaEventRecord(ctx->ev_out[c], ctx->s_out));
     } else if (ctx->trace) {
@@ -1351,8 +1373,8 @@ int noahmp_b200_output_begin(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, con
   off = 0;
   for (int f : list) {
     const size_t n = (size_t)ctx->ncell * kFields[f].layers;
-    pin(ctx, host_ptr(a, f), n * sizeof(float));
-    CK(cudaMemcpyAsync(host_ptr(a, f), ctx->d_outstage + off, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
+    pin(ctx, host_ptr(a, f), host_bytes(ctx, kFields[f].layers));
+    CK(copy_field_rows(ctx, ctx->d_outstage + off, host_ptr(a, f), kFields[f].layers, 0, ctx->nj, false, ctx->s_out));
     off += n;
   }
   CK(cudaEventRecord(ctx->ev_outdone, ctx->s_out));
@@ -1425,9 +1447,10 @@ int noahmp_b200_fetch(noahmp_b200_ctx* ctx, const noahmp_lsm_args* a, const char
     ctx->launches++;
   }
   float* dst = host_ptr(a, f);
-  const size_t bytes = sizeof(float) * ctx->ncell * kFields[f].layers;
-  pin(ctx, dst, bytes);
-  CK(cudaMemcpyAsync(dst, ctx->d_grid[f], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = check_bounds(ctx, a);
+  if (rc) return rc;
+  pin(ctx, dst, host_bytes(ctx, kFields[f].layers));
+  CK(copy_field_rows(ctx, ctx->d_grid[f], dst, kFields[f].layers, 0, ctx->nj, false, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -1483,11 +1506,17 @@ static inline float* wt_ptr(const noahmp_wtable_args* a, size_t off) {
 static int wt_check(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
   if (!ctx || !a) return NOAHMP_ERR_ARG;
   if (!ctx->uploaded) { set_error("wtable before the state was uploaded (call noahmplsm or upload first)"); return NOAHMP_ERR_ARG; }
-  if (a->ims != a->its || a->ime != a->ite || a->jms != a->jts || a->jme != a->jte ||
+  if (a->ims > a->its || a->ime < a->ite || a->jms > a->jts || a->jme < a->jte ||
       a->ite - a->its + 1 != ctx->ni || a->jte - a->jts + 1 != ctx->nj || a->nsoil != NOAHMP_NSOIL) {
-    set_error("wtable: memory bounds must equal tile bounds and match the context");
+    set_error("wtable: memory bounds must contain the tile bounds and the tile must match the context");
     return NOAHMP_ERR_ARG;
   }
+  ctx->h_mi = a->ime - a->ims + 1;
+  ctx->h_mj = a->jme - a->jms + 1;
+  ctx->h_x0 = a->its - a->ims;
+  ctx->h_y0 = a->jts - a->jms;
+  ctx->h_its = a->its;
+  ctx->h_jts = a->jts;
   return 0;
 }
 
@@ -1543,10 +1572,13 @@ static int wt_prepare(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
     const float* src[NWT] = {a->fdepth, a->area, a->topo, a->rivercond, a->riverbed, a->eqwtd, a->pexp, nullptr, nullptr,
                              a->qslat, a->qrfs, a->qsprings};
     for (int k = 0; k < NWT; ++k)
-      if (src[k]) { pin(ctx, src[k], plane); CK(cudaMemcpyAsync(ctx->d_wt[k], src[k], plane, cudaMemcpyHostToDevice, ctx->stream)); }
+      if (src[k]) {
+        pin(ctx, src[k], host_bytes(ctx, 1));
+        CK(copy_field_rows(ctx, ctx->d_wt[k], const_cast<float*>(src[k]), 1, 0, ctx->nj, true, ctx->stream));
+      }
     // SMOISEQ is static input of the scheme
-    pin(ctx, a->smoiseq, plane * NOAHMP_NSOIL);
-    CK(cudaMemcpyAsync(ctx->d_grid[F_smoiseq], a->smoiseq, plane * NOAHMP_NSOIL, cudaMemcpyHostToDevice, ctx->stream));
+    pin(ctx, a->smoiseq, host_bytes(ctx, NOAHMP_NSOIL));
+    CK(copy_field_rows(ctx, ctx->d_grid[F_smoiseq], const_cast<float*>(a->smoiseq), NOAHMP_NSOIL, 0, ctx->nj, true, ctx->stream));
     if ((rc = gather_field(ctx, F_smoiseq))) return rc;
     ctx->wt_init = true;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1597,12 +1629,10 @@ int noahmp_b200_wtable_begin(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) 
   CK(cudaSetDevice(ctx->device));
   ++ctx->pin_clock;
   if ((rc = wt_prepare(ctx, a))) return rc;
-  const size_t plane = sizeof(float) * ctx->ncell;
   if (ctx->sync_mode == NOAHMP_SYNC_FULL) {
     for (const WtField& wf : kWtInout) {
-      const size_t bytes = plane * kFields[wf.f].layers;
-      pin(ctx, wt_ptr(a, wf.off), bytes);
-      CK(cudaMemcpyAsync(ctx->d_grid[wf.f], wt_ptr(a, wf.off), bytes, cudaMemcpyHostToDevice, ctx->stream));
+      pin(ctx, wt_ptr(a, wf.off), host_bytes(ctx, kFields[wf.f].layers));
+      CK(copy_field_rows(ctx, ctx->d_grid[wf.f], wt_ptr(a, wf.off), kFields[wf.f].layers, 0, ctx->nj, true, ctx->stream));
       if ((rc = gather_field(ctx, wf.f))) return rc;
     }
   } else {
@@ -1621,19 +1651,17 @@ int noahmp_b200_wtable_halo(noahmp_b200_ctx* ctx, float** kcell, float** head) {
 }
 
 static int wt_download(noahmp_b200_ctx* ctx, const noahmp_wtable_args* a) {
-  const size_t plane = sizeof(float) * ctx->ncell;
   int rc;
   for (const WtField& wf : kWtInout) {
     if ((rc = scatter_field(ctx, wf.f))) return rc;
-    const size_t bytes = plane * kFields[wf.f].layers;
-    pin(ctx, wt_ptr(a, wf.off), bytes);
-    CK(cudaMemcpyAsync(wt_ptr(a, wf.off), ctx->d_grid[wf.f], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    pin(ctx, wt_ptr(a, wf.off), host_bytes(ctx, kFields[wf.f].layers));
+    CK(copy_field_rows(ctx, ctx->d_grid[wf.f], wt_ptr(a, wf.off), kFields[wf.f].layers, 0, ctx->nj, false, ctx->stream));
   }
   float* dst[5] = {a->qrf, a->qspring, a->qslat, a->qrfs, a->qsprings};
   const int src[5] = {WT_QRF, WT_QSPRING, WT_QSLAT, WT_QRFS, WT_QSPRINGS};
   for (int k = 0; k < 5; ++k) {
-    pin(ctx, dst[k], plane);
-    CK(cudaMemcpyAsync(dst[k], ctx->d_wt[src[k]], plane, cudaMemcpyDeviceToHost, ctx->stream));
+    pin(ctx, dst[k], host_bytes(ctx, 1));
+    CK(copy_field_rows(ctx, ctx->d_wt[src[k]], dst[k], 1, 0, ctx->nj, false, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -1715,19 +1743,26 @@ int noahmp_b200_comm_init(noahmp_b200_ctx* ctx, const void* id128, int rank, int
   NK(N->CommInitRank(&ctx->comm.comm, nranks, id, rank));
   NmpComm& C = ctx->comm;
   C.rank = rank; C.nranks = nranks;
-  int npx, npy;
-  noahmp_b200_proc_grid(nranks, &npx, &npy);
-  const int ipx = rank % npx, ipy = rank / npx;
-  C.left = ipx > 0 ? rank - 1 : -1;
-  C.right = ipx < npx - 1 ? rank + 1 : -1;
-  C.down = ipy > 0 ? rank - npx : -1;
-  C.up = ipy < npy - 1 ? rank + npx : -1;
+  int nb[4];
+  noahmp_b200_tile_neighbours(nranks, rank, nb);
+  C.left = nb[0]; C.right = nb[1]; C.down = nb[2]; C.up = nb[3];
   if (!C.d_send) {
     CK(cudaMalloc(&C.d_send, sizeof(float) * 4 * (size_t)ctx->nj));
     CK(cudaMalloc(&C.d_recv, sizeof(float) * 4 * (size_t)ctx->nj));
     CK(cudaMalloc(&C.d_budget_sum, sizeof(double) * NBUDGET));
   }
   return 0;
+}
+
+// ranks of the tiles left, right, below (smaller j) and above `rank` in the mpp_land process grid; -1 at the edge
+void noahmp_b200_tile_neighbours(int nranks, int rank, int nb[4]) {
+  int npx, npy;
+  noahmp_b200_proc_grid(nranks, &npx, &npy);
+  const int ipx = rank % npx, ipy = rank / npx;
+  nb[0] = ipx > 0 ? rank - 1 : -1;
+  nb[1] = ipx < npx - 1 ? rank + 1 : -1;
+  nb[2] = ipy > 0 ? rank - npx : -1;
+  nb[3] = ipy < npy - 1 ? rank + npx : -1;
 }
 
 int noahmp_b200_comm_neighbours(const noahmp_b200_ctx* ctx, int nb[4]) {
@@ -2094,6 +2129,135 @@ void noahmp_b200_tile(int global_nx, int global_ny, int nproc, int rank, int* xs
   };
   split(global_nx, npx, ipx, xstart, xend);
   split(global_ny, npy, ipy, ystart, yend);
+}
+
+// ---- one host process, several GPUs (row f4) --------------------------------------------------------------------------
+// Replaces the reference's IO-rank data path — decompose_data_real / _int scatter the global arrays read by rank 0 to
+// the MPI ranks and write_io_real / _int gather them back for output (mpp/module_mpp_land.F90:645-857) — by direct tile
+// slicing: the process keeps the WHOLE-domain arrays, each GPU owns the tile mpp_land_partition_calc would give it, and
+// every context copies its own rows straight out of / into the global arrays (pitched copies, memory extent = domain,
+// tile bounds = the GPU's tile).  One worker thread per GPU drives its context, so the tiles' pipelines run concurrently.
+struct noahmp_b200_domain {
+  int gni = 0, gnj = 0, ntiles = 0;
+  std::vector<noahmp_b200_ctx*> tile;
+  std::vector<int> xs, xe, ys, ye;
+};
+
+noahmp_b200_domain* noahmp_b200_domain_create(const noahmp_tables* tables, int global_ni, int global_nj, int ntiles,
+                                              const int* devices) {
+  if (!tables || global_ni <= 0 || global_nj <= 0 || ntiles <= 0 || !devices) {
+    set_error("bad arguments to noahmp_b200_domain_create");
+    return nullptr;
+  }
+  auto* d = new noahmp_b200_domain();
+  d->gni = global_ni; d->gnj = global_nj; d->ntiles = ntiles;
+  d->xs.resize(ntiles); d->xe.resize(ntiles); d->ys.resize(ntiles); d->ye.resize(ntiles);
+  for (int r = 0; r < ntiles; ++r) {
+    noahmp_b200_tile(global_ni, global_nj, ntiles, r, &d->xs[r], &d->xe[r], &d->ys[r], &d->ye[r]);
+    noahmp_b200_ctx* c = noahmp_b200_create(devices[r], tables, d->xe[r] - d->xs[r] + 1, d->ye[r] - d->ys[r] + 1);
+    if (!c) { noahmp_b200_domain_destroy(d); return nullptr; }
+    d->tile.push_back(c);
+  }
+  return d;
+}
+
+void noahmp_b200_domain_destroy(noahmp_b200_domain* d) {
+  if (!d) return;
+  for (auto* c : d->tile) noahmp_b200_destroy(c);
+  delete d;
+}
+
+int noahmp_b200_domain_ntiles(const noahmp_b200_domain* d) { return d ? d->ntiles : 0; }
+noahmp_b200_ctx* noahmp_b200_domain_tile(noahmp_b200_domain* d, int r) {
+  return (d && r >= 0 && r < d->ntiles) ? d->tile[r] : nullptr;
+}
+int noahmp_b200_domain_tile_bounds(const noahmp_b200_domain* d, int r, int* xs, int* xe, int* ys, int* ye) {
+  if (!d || r < 0 || r >= d->ntiles) return NOAHMP_ERR_ARG;
+  *xs = d->xs[r]; *xe = d->xe[r]; *ys = d->ys[r]; *ye = d->ye[r];
+  return 0;
+}
+
+// args of tile r: the caller's global arrays and memory bounds, tile bounds of the GPU's tile
+static noahmp_lsm_args domain_tile_args(const noahmp_b200_domain* d, const noahmp_lsm_args* g, int r) {
+  noahmp_lsm_args a = *g;
+  a.its = g->ims + d->xs[r] - 1; a.ite = g->ims + d->xe[r] - 1;
+  a.jts = g->jms + d->ys[r] - 1; a.jte = g->jms + d->ye[r] - 1;
+  return a;
+}
+static int domain_check(const noahmp_b200_domain* d, const noahmp_lsm_args* g) {
+  if (!d || !g) return NOAHMP_ERR_ARG;
+  if (g->ime - g->ims + 1 != d->gni || g->jme - g->jms + 1 != d->gnj) {
+    set_error("domain call: the memory bounds must span the whole domain the domain object was created for");
+    return NOAHMP_ERR_ARG;
+  }
+  return 0;
+}
+
+}  // extern "C"
+template <class F>
+static int domain_for_tiles(noahmp_b200_domain* d, F&& fn) {
+  std::vector<int> rc(d->ntiles, 0);
+  std::vector<std::string> err(d->ntiles);
+  std::vector<std::thread> th;
+  for (int r = 0; r < d->ntiles; ++r)
+    th.emplace_back([&, r] {
+      rc[r] = fn(r);
+      if (rc[r] >= NOAHMP_ERR_CUDA) err[r] = g_last_error;  // thread-local message of the worker
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < d->ntiles; ++r)
+    if (rc[r] >= NOAHMP_ERR_CUDA) { set_error("tile " + std::to_string(r) + ": " + err[r]); return rc[r]; }
+  return 0;
+}
+extern "C" {
+
+// CALL noahmplsm(...) on the whole domain: `g` describes the global arrays (ims:ime x jms:jme = the domain).
+// status: the first failing column in the reference's loop order (j outer, i inner) and the total count.
+int noahmp_b200_domain_noahmplsm(noahmp_b200_domain* d, const noahmp_lsm_args* g, noahmp_status* status) {
+  int rc = domain_check(d, g);
+  if (rc) return rc;
+  std::vector<noahmp_status> st(d->ntiles);
+  rc = domain_for_tiles(d, [&](int r) {
+    noahmp_lsm_args a = domain_tile_args(d, g, r);
+    return noahmp_b200_noahmplsm(d->tile[r], &a, &st[r]);
+  });
+  if (rc) return rc;
+  noahmp_status out{0, 0, 0, 0, 0.f};
+  for (int r = 0; r < d->ntiles; ++r) {
+    if (!st[r].code) continue;
+    out.count += st[r].count;
+    if (!out.code || st[r].j < out.j || (st[r].j == out.j && st[r].i < out.i)) {
+      const int n = out.count;
+      out = st[r];
+      out.count = n;
+    }
+  }
+  if (status) *status = out;
+  return out.code;
+}
+
+int noahmp_b200_domain_sync_host(noahmp_b200_domain* d, const noahmp_lsm_args* g) {
+  int rc = domain_check(d, g);
+  if (rc) return rc;
+  return domain_for_tiles(d, [&](int r) {
+    noahmp_lsm_args a = domain_tile_args(d, g, r);
+    return noahmp_b200_sync_host(d->tile[r], &a);
+  });
+}
+
+// settings applied to every tile
+int noahmp_b200_domain_configure(noahmp_b200_domain* d, int sync_mode, int math_mode, const char* fetch, const char* push,
+                                 unsigned hints) {
+  if (!d) return NOAHMP_ERR_ARG;
+  for (auto* c : d->tile) {
+    int rc;
+    if ((rc = noahmp_b200_set_mode(c, sync_mode))) return rc;
+    if ((rc = noahmp_b200_set_math(c, math_mode))) return rc;
+    if (fetch && (rc = noahmp_b200_set_fetch(c, fetch))) return rc;
+    if (push && (rc = noahmp_b200_set_push(c, push))) return rc;
+    if ((rc = noahmp_b200_set_forcing_hints(c, hints))) return rc;
+  }
+  return 0;
 }
 
 }  // extern "C"

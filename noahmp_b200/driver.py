@@ -45,6 +45,13 @@ def proc_grid(nproc):
     return nx.value, ny.value
 
 
+def tile_neighbours(nproc, rank):
+    """(left, right, below, above) ranks of the neighbouring tiles in the mpp_land process grid, -1 at the edge."""
+    nb = (C.c_int * 4)()
+    _lib.lib().noahmp_b200_tile_neighbours(nproc, rank, nb)
+    return tuple(nb)
+
+
 def tile(global_nx, global_ny, nproc, rank):
     """(xstart, xend, ystart, yend), 1-based inclusive, of `rank` (mpp_land_partition_calc)."""
     v = [C.c_int() for _ in range(4)]
@@ -393,3 +400,58 @@ class NoahMP:
         out = np.empty((self.nj, self.ni), np.int32)
         self._check(self._L.noahmp_b200_get_iteration_counts(self._ctx, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
+
+
+class NoahMPDomain:
+    """One host process, several GPUs: the process holds the WHOLE-domain arrays, tile r of the
+    mpp_land partition lives on devices[r], and every call slices the tiles straight out of / into the global arrays
+    (noahmp_b200_domain_*).  `devices` may name a GPU more than once (several tiles per GPU)."""
+
+    def __init__(self, tables, ni, nj, devices, sync=SYNC_FULL, math=MATH_FAST, fetch=None, push=None, hints=0):
+        self._L = _lib.lib()
+        if isinstance(tables, dict):
+            tables = _capi.tables_from_dict(tables)
+        self.tables, self.ni, self.nj, self.devices = tables, ni, nj, list(devices)
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        self._d = self._L.noahmp_b200_domain_create(C.byref(tables), ni, nj, len(self.devices), dev)
+        if not self._d:
+            raise NoahmpError(100, self._L.noahmp_b200_last_error().decode())
+        rc = self._L.noahmp_b200_domain_configure(
+            self._d, sync, math, None if fetch is None else ",".join(fetch).encode(),
+            None if push is None else ",".join(push).encode(), int(hints))
+        if rc:
+            raise NoahmpError(rc, self._L.noahmp_b200_last_error().decode())
+        self._keep = None
+
+    @property
+    def ntiles(self):
+        return self._L.noahmp_b200_domain_ntiles(self._d)
+
+    def tile_bounds(self, r):
+        v = [C.c_int() for _ in range(4)]
+        self._L.noahmp_b200_domain_tile_bounds(self._d, r, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def _check(self, rc):
+        if rc in (100, 101, 8):
+            raise NoahmpError(rc, self._L.noahmp_b200_last_error().decode())
+        return rc
+
+    def noahmplsm(self, arrays, scalars):
+        """CALL noahmplsm(...) with the global arrays; scalars carry the domain as memory bounds (ims..jme)."""
+        self._keep = arrays
+        a = _capi.make_args(arrays, scalars)
+        st = _capi.NoahmpStatus()
+        self._check(self._L.noahmp_b200_domain_noahmplsm(self._d, C.byref(a), C.byref(st)))
+        return st
+
+    def sync_host(self, arrays, scalars):
+        a = _capi.make_args(arrays, scalars)
+        self._check(self._L.noahmp_b200_domain_sync_host(self._d, C.byref(a)))
+
+    def close(self):
+        if getattr(self, "_d", None):
+            self._L.noahmp_b200_domain_destroy(self._d)
+            self._d = None
+
+    __del__ = close

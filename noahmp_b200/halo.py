@@ -23,6 +23,24 @@ def neighbours(rank, world):
     return left, right, down, up
 
 
+def allreduce_budget(sums):
+    """Host-side form of the global water / energy budget for a driver whose ranks talk through torch.distributed
+    (any backend) instead of the library's own NCCL communicator: sums = the dict NoahMP.budget_read() returns for this
+    tile; returns the dict summed over all ranks ('steps' is the common step count, not a sum)."""
+    names = list(sums)
+    v = torch.tensor([float(sums[n]) for n in names], dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == "nccl":
+            v = v.cuda()
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        v = v.cpu()
+        out = dict(zip(names, v.tolist()))
+        if "steps" in out:
+            out["steps"] /= dist.get_world_size()
+        return out
+    return dict(zip(names, v.tolist()))
+
+
 def _exchange(pairs):
     """pairs: list of (peer, send_tensor, recv_tensor). Ordered so that lower ranks send first (deadlock-free on
     backends without batched p2p); uses batch_isend_irecv where available."""

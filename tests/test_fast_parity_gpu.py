@@ -24,12 +24,16 @@ from helpers import clone_state, make_case, run_gpu, run_oracle
 
 # name -> (tolerance, allowed fraction of columns outside it, hard cap on any column)
 FAST_TOL = {
-    "tsk": (0.05, 5e-3, 6.0), "tslb": (0.02, 5e-3, 3.0), "smois": (5e-4, 5e-3, 0.05), "sh2o": (5e-4, 5e-3, 0.05),
-    "snow": (0.05, 5e-3, 5.0), "snowh": (1e-3, 5e-3, 0.06), "hfx": (1.0, 1e-2, 150.0), "lh": (1.0, 1e-2, 150.0),
-    "grdflx": (1.0, 1e-2, 200.0), "sfcrunoff": (0.02, 5e-3, 5.0), "udrunoff": (0.02, 5e-3, 5.0),
-    "xlaixy": (2e-3, 5e-3, 0.1),
+    "tsk": (0.05, 2e-3, 4.0), "tslb": (0.05, 5e-3, 1.5), "smois": (5e-4, 2e-3, 0.05), "sh2o": (5e-4, 2e-3, 0.05),
+    "snow": (0.05, 2e-3, 4.0), "snowh": (1e-3, 2e-3, 0.025), "hfx": (1.0, 2e-3, 100.0), "lh": (1.0, 2e-3, 150.0),
+    "grdflx": (1.0, 2e-3, 100.0), "sfcrunoff": (0.02, 2e-3, 1.0), "udrunoff": (0.02, 2e-3, 0.5),
+    "xlaixy": (2e-3, 2e-3, 0.05),
 }
-ISNOW_MISMATCH = 5e-3  # largest fraction of columns whose snow-layer count may differ
+# Measured on a B200 (profiles/r02_fast_accuracy.json; 37 k / 13 k land + 4 k glacier columns, up to 240 steps): largest
+# differences seen TSK 1.3 K (one column, a Newton-exit flip that decays within hours; p99.9 0.014 K), TSLB 0.46 K
+# (p99.9 0.06 K: snow-pack phase change), SNOW 1.45 mm, SNOWH 7 mm (cap = one snow-layer threshold, 0.025 m), HFX / LH
+# 24 / 58 W/m2 (p99.9 0.4), runoff 0.18 mm, LAI 0.002; ISNOWXY differed in 1.5e-4 of the columns after 240 steps.
+ISNOW_MISMATCH = 2e-3  # largest fraction of columns whose snow-layer count may differ
 
 pytestmark = pytest.mark.gpu
 

@@ -72,3 +72,48 @@ def test_tiled_run_equals_single_domain(built, tables_usgs, tmp_path, world):
         assert np.array_equal(z["isnow"], state["isnowxy"][ys - 1:ye, xs - 1:xe])
         seen[ys - 1:ye, xs - 1:xe] = True
     assert seen.all()
+
+
+def _budget_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from noahmp_b200 import halo
+    names = ("storage_mm", "precip_mm", "et_mm", "runoff_mm", "erreng_wm2", "swe_mm", "columns", "steps")
+    local = {n: float((rank + 1) * (k + 1)) for k, n in enumerate(names)}
+    local["steps"] = 24.0
+    out = halo.allreduce_budget(local)
+    np.save(os.path.join(outdir, f"b{rank}.npy"), np.array([out[n] for n in names]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_budget_allreduce_over_gloo(tmp_path, world):
+    """Row e3, host-side form: eight fp64 budget sums per tile, one all-reduce (SUM); every rank ends with the same
+    global sums and the common step count.  (On the GPU box the library does the same with one ncclAllReduce:
+    tests/test_multigpu.py.)"""
+    mp.spawn(_budget_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = np.array([sum((r + 1) * (k + 1) for r in range(world)) for k in range(8)], float)
+    want[7] = 24.0
+    for r in range(world):
+        assert np.array_equal(np.load(os.path.join(tmp_path, f"b{r}.npy")), want)
+
+
+def test_tile_neighbours_match_the_process_grid():
+    import noahmp_b200
+    from noahmp_b200 import halo
+    for world in (1, 2, 3, 4, 6, 8, 12, 16):
+        npx, npy = noahmp_b200.proc_grid(world)
+        for r in range(world):
+            nb = noahmp_b200.tile_neighbours(world, r)
+            assert nb == tuple(-1 if x is None else x for x in halo.neighbours(r, world))
+            ipx, ipy = r % npx, r // npx
+            assert (nb[0] >= 0) == (ipx > 0) and (nb[1] >= 0) == (ipx < npx - 1)
+            assert (nb[2] >= 0) == (ipy > 0) and (nb[3] >= 0) == (ipy < npy - 1)
+            if nb[1] >= 0:  # neighbours in a process row share the tile height; in a process column, the width
+                a, b = noahmp_b200.tile(101, 67, world, r), noahmp_b200.tile(101, 67, world, nb[1])
+                assert (a[2], a[3]) == (b[2], b[3]) and b[0] == a[1] + 1
+            if nb[3] >= 0:
+                a, b = noahmp_b200.tile(101, 67, world, r), noahmp_b200.tile(101, 67, world, nb[3])
+                assert (a[0], a[1]) == (b[0], b[1]) and b[2] == a[3] + 1

@@ -1,4 +1,4 @@
-"""Time the device-resident step of several builds of the library (tools/build_variant.sh) on one GPU.
+"""Time the device-resident step (24 steps = one diurnal cycle) of several builds of the library (tools/build_variant.sh) on one GPU.
 usage: python tools/time_variants.py NI NJ name1 name2 ...   (name 'main' = libnoahmp_b200.so)"""
 import json, os, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +8,7 @@ for name in sys.argv[3:]:
     env = dict(os.environ)
     if name != "main":
         env["NOAHMP_B200_LIB"] = os.path.join(root, "noahmp_b200", f"libnoahmp_b200_{name}.so")
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--grid", ni, nj, "--steps", "6", "--warmup",
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--grid", ni, nj, "--steps", "24", "--warmup",
                           "3", "--no-e2e", "--no-cpu-baseline"], env=env, capture_output=True, text=True)
     try:
         line = json.loads(out.stdout.strip().splitlines()[-1])
