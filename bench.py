@@ -504,20 +504,28 @@ def main():
         # op-counting instantiation of the oracle on this workload (tools/opcount.py), not executed instructions.
         if opc.get(cfg.name if cfg.name != "C5" else "C3") and peaks:
             o = opc[cfg.name if cfg.name != "C5" else "C3"]
+            hrs = [o["by_hour_utc"][str((cfg.start[3] + h) % 24)] for h in timed_hours]
+            fp32_pc = float(np.mean([x["fp32_instr"] for x in hrs]))
+            fp32u_pc = float(np.mean([x["fp32_instr_unfused"] for x in hrs]))
+            mufu_pc = float(np.mean([x["mufu"] for x in hrs]))
             colrate = ncol / (mean_ms * 1e-3)
-            fp32 = o["fp32_instr_per_column_step"] * colrate
-            mufu = o["mufu_per_column_step"] * colrate
+            fpk, mpk = peaks["ffma_thread_instr_per_s"], peaks["mufu_ex2_thread_instr_per_s"]
+            f_fp32, f_mufu = fp32_pc * colrate / fpk, mufu_pc * colrate / mpk
+            f_issue = (fp32_pc + mufu_pc) * colrate / fpk
             line["compute_roofline"] = {
-                "bound": "fp32/sfu issue",
-                "fp32_instr_per_column_step": o["fp32_instr_per_column_step"], "mufu_per_column_step": o["mufu_per_column_step"],
-                "fp32": {"achieved_thread_instr_per_s": fp32, "peak": peaks["ffma_thread_instr_per_s"],
-                         "frac": fp32 / peaks["ffma_thread_instr_per_s"]},
-                "mufu": {"achieved_thread_instr_per_s": mufu, "peak": peaks["mufu_ex2_thread_instr_per_s"],
-                         "frac": mufu / peaks["mufu_ex2_thread_instr_per_s"]},
-                "frac": fp32 / peaks["ffma_thread_instr_per_s"] + mufu / peaks["mufu_ex2_thread_instr_per_s"],
-                "source": "operation counts: profiles/r02_opcount.json (op-counting oracle, " + o.get("sample", "") +
-                          "); peaks: profiles/r01_peaks.json (tools/peaks.cu on this GPU type); frac = share of the SM's "
-                          "issue time the algorithmic FP32 and MUFU work needs at those rates"}
+                "bound": "sfu (MUFU pipe)" if f_mufu >= f_issue else "fp32 issue",
+                "frac": max(f_mufu, f_issue),
+                "fp32_instr_per_column_step": fp32_pc, "fp32_instr_unfused_per_column_step": fp32u_pc,
+                "mufu_per_column_step": mufu_pc,
+                "mufu": {"achieved_thread_instr_per_s": mufu_pc * colrate, "peak": mpk, "frac": f_mufu},
+                "fp32": {"achieved_thread_instr_per_s": fp32_pc * colrate, "peak": fpk, "frac": f_fp32},
+                "issue": {"achieved_thread_instr_per_s": (fp32_pc + mufu_pc) * colrate, "peak": fpk, "frac": f_issue},
+                "source": "ALGORITHMIC operations per column-step counted by the op-counting instantiation of the oracle "
+                          "on the timed hours (tools/opcount.py -> profiles/r02_opcount.json: " + o.get("sample", "") + "); "
+                          "fp32_instr assumes every add fuses with a multiply (lower bound), divisions and transcendentals "
+                          "expanded as the production build issues them; peaks = measured FFMA and MUFU.EX2 issue rates of "
+                          "this GPU type (tools/peaks.cu, profiles/r01_peaks.json); frac = the larger of the MUFU-pipe and "
+                          "the issue-slot fraction"}
         if kc.get("warp_instr_per_column"):
             wi = kc["warp_instr_per_column"] * ncol / (mean_ms * 1e-3)
             issue_peak = (peaks.get("ffma_thread_instr_per_s") or N_SM * SCHED_PER_SM * 32 * 1.965e9) / 32.0

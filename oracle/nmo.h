@@ -24,23 +24,27 @@ namespace nmo {
 
 // ---- math backend: 0 = host libm (what the reference links), 1 = portable nmp_math.h --------
 extern int g_math_mode;
-inline float EXP(float x)   { return g_math_mode ? nmpm::expf_(x)   : std::exp(x); }
-inline float LOG(float x)   { return g_math_mode ? nmpm::logf_(x)   : std::log(x); }
-inline float LOG10(float x) { return g_math_mode ? nmpm::log10f_(x) : std::log10(x); }
-inline float POW(float x, float y) { return g_math_mode ? nmpm::powf_(x, y) : std::pow(x, y); }
-inline double DPOW(double x, double y) { return g_math_mode ? nmpm::pow_d(x, y) : std::pow(x, y); }
-inline float ATAN(float x)  { return g_math_mode ? nmpm::atanf_(x)  : std::atan(x); }
-inline float TAN(float x)   { return g_math_mode ? nmpm::tanf_(x)   : std::tan(x); }
-inline float COS(float x)   { return g_math_mode ? nmpm::cosf_(x)   : std::cos(x); }
-inline float SIN(float x)   { return g_math_mode ? nmpm::sinf_(x)   : std::sin(x); }
-inline float ASIN(float x)  { return g_math_mode ? nmpm::asinf_(x)  : std::asin(x); }
-inline float ACOS(float x)  { return g_math_mode ? nmpm::acosf_(x)  : std::acos(x); }
-inline float TANH(float x)  { return g_math_mode ? nmpm::tanhf_(x)  : std::tanh(x); }
-inline float SQRT(float x)  { return std::sqrt(x); }
+// op-counting instantiation (nmo_count.h): every transcendental call is tallied by class; a no-op otherwise
+#ifndef NMO_TICK
+#define NMO_TICK(cls) ((void)0)
+#endif
+inline float EXP(float x)   { NMO_TICK(EXP); return g_math_mode ? nmpm::expf_(x)   : std::exp(x); }
+inline float LOG(float x)   { NMO_TICK(LOG); return g_math_mode ? nmpm::logf_(x)   : std::log(x); }
+inline float LOG10(float x) { NMO_TICK(LOG10); return g_math_mode ? nmpm::log10f_(x) : std::log10(x); }
+inline float POW(float x, float y) { NMO_TICK(POW); return g_math_mode ? nmpm::powf_(x, y) : std::pow(x, y); }
+inline double DPOW(double x, double y) { NMO_TICK(DPOW); return g_math_mode ? nmpm::pow_d(x, y) : std::pow(x, y); }
+inline float ATAN(float x)  { NMO_TICK(ATAN); return g_math_mode ? nmpm::atanf_(x)  : std::atan(x); }
+inline float TAN(float x)   { NMO_TICK(TAN); return g_math_mode ? nmpm::tanf_(x)   : std::tan(x); }
+inline float COS(float x)   { NMO_TICK(COS); return g_math_mode ? nmpm::cosf_(x)   : std::cos(x); }
+inline float SIN(float x)   { NMO_TICK(SIN); return g_math_mode ? nmpm::sinf_(x)   : std::sin(x); }
+inline float ASIN(float x)  { NMO_TICK(ASIN); return g_math_mode ? nmpm::asinf_(x)  : std::asin(x); }
+inline float ACOS(float x)  { NMO_TICK(ACOS); return g_math_mode ? nmpm::acosf_(x)  : std::acos(x); }
+inline float TANH(float x)  { NMO_TICK(TANH); return g_math_mode ? nmpm::tanhf_(x)  : std::tanh(x); }
+inline float SQRT(float x)  { NMO_TICK(SQRT); return std::sqrt(x); }
 // integer power x**n exactly as libgcc's __powisf2 evaluates it (square-and-multiply)
 inline float POWI(float x, int m) {
   unsigned n = m < 0 ? -(unsigned)m : (unsigned)m;
-  float y = (n & 1) ? x : 1.0f;
+  float y = (n & 1) ? x : float(1.0f);
   while (n >>= 1) { x = x * x; if (n & 1) y *= x; }
   return m < 0 ? 1.0f / y : y;
 }
@@ -105,9 +109,14 @@ struct Ctx {
   void fatal(int code, float v) { if (!err_code) { err_code = code; err_value = v; } }
 };
 
-// 1-based accessors for the table struct
-inline float TV1(const float* a, int vegtyp) { return a[vegtyp - 1]; }
-inline float TV2(const float (*a)[NOAHMP_MVT], int vegtyp, int k) { return a[k - 1][vegtyp - 1]; }
+// 1-based accessors for the table struct (tblf: the tables' plain fp32 words, also in the op-counting instantiation)
+#ifdef NMO_OPCOUNT
+typedef nmo_count::true_float tblf;
+#else
+typedef float tblf;
+#endif
+inline float TV1(const tblf* a, int vegtyp) { return a[vegtyp - 1]; }
+inline float TV2(const tblf (*a)[NOAHMP_MVT], int vegtyp, int k) { return a[k - 1][vegtyp - 1]; }
 
 int REDPRM(Ctx& c, int VEGTYP, int SOILTYP, int SLOPETYP, const ASoil& ZSOIL, int ISURBAN);
 

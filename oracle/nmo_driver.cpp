@@ -367,6 +367,6 @@ void nmo_rosr12(int n, const float* a, const float* b, const float* c, const flo
 void nmo_combo(float* v, const float* w) { nmo::COMBO(v[0], v[1], v[2], v[3], w[0], w[1], w[2], w[3]); }
 
 void nmo_math_array(int fn, const float* x, const float* y, float* out, long n) {
-  for (long i = 0; i < n; ++i) out[i] = nmo_math1(fn, x[i], y ? y[i] : 0.f);
+  for (long i = 0; i < n; ++i) out[i] = nmo_math1(fn, x[i], y ? y[i] : float(0.f));
 }
 }
