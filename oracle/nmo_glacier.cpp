@@ -727,3 +727,21 @@ void NOAHMP_GLACIER(Ctx& c, GlacIO& g) {
 }
 
 }  // namespace nmo
+
+extern "C" {
+// PHASECHANGE_GLACIER probe (glacier.F90:1635-1922): arrays in the oracle's Fortran bounds packed from the lowest index
+void nmo_phasechange_glacier(int ISNOW, float DT, const float* FACT7, const float* DZSNSO7, float* STC7, float* SNICE3,
+                             float* SNLIQ3, float* SNEQV, float* SNOWH, float* SMC4, float* SH2O4, float* QMELT, int* IMELT7,
+                             float* PONDING) {
+  using namespace nmo;
+  ASnSo fact, dz, stc; ASnow ice, liq; ASoil smc, sh; IA<-NSNOW + 1, NSOIL> im;
+  for (int k = -2; k <= NSOIL; ++k) { fact(k) = FACT7[k + 2]; dz(k) = DZSNSO7[k + 2]; stc(k) = STC7[k + 2]; im(k) = 0; }
+  for (int k = -2; k <= 0; ++k) { ice(k) = SNICE3[k + 2]; liq(k) = SNLIQ3[k + 2]; }
+  for (int k = 1; k <= NSOIL; ++k) { smc(k) = SMC4[k - 1]; sh(k) = SH2O4[k - 1]; }
+  PHASECHANGE_GLACIER(ISNOW, DT, fact, dz, stc, ice, liq, *SNEQV, *SNOWH, smc, sh, *QMELT, im, *PONDING);
+  for (int k = -2; k <= NSOIL; ++k) { STC7[k + 2] = stc(k); IMELT7[k + 2] = im(k); }
+  for (int k = -2; k <= 0; ++k) { SNICE3[k + 2] = ice(k); SNLIQ3[k + 2] = liq(k); }
+  for (int k = 1; k <= NSOIL; ++k) { SMC4[k - 1] = smc(k); SH2O4[k - 1] = sh(k); }
+}
+}
+

@@ -899,5 +899,11 @@ float nmo_frh2o(float TKELV, float SMC, float SH2O, float BEXP, float PSISAT, fl
   nmo::FRH2O(c, FREE, TKELV, SMC, SH2O);
   return FREE;
 }
+// STOMATA: in = {APAR FOLN TV EI EA SFCTMP SFCPRS O2 CO2 IGS BTRAN RB}; out = {RS PSN}
+void nmo_stomata(const noahmp_tables* T, int VEGTYP, const float* in, float* out2) {
+  nmo::Ctx c{};
+  c.T = T;
+  nmo::STOMATA(c, VEGTYP, 1.E-6f, in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], in[8], in[9], in[10], in[11],
+               out2[0], out2[1]);
 }
-
+}

@@ -1149,3 +1149,63 @@ int REDPRM(Ctx& c, int VEGTYP, int SOILTYP, int SLOPETYP, const ASoil& ZSOIL, in
 }
 
 }  // namespace nmo
+
+// ---- probes for the known-answer / conservation tests of the WATER side (tests/test_oracle_water.py) ----------------
+extern "C" {
+// CANWATER: in = {DT SFCTMP UU VV FCEV FCTR QPRECC QPRECL ELAI ESAI TG FVEG frozen_canopy}, io = {CANLIQ CANICE TV},
+// out = {CMC ECAN ETRAN QRAIN QSNOW SNOWHIN FWET FPICE}
+void nmo_canwater(const noahmp_tables* T, int opt_snf, int VEGTYP, const float* in, float* io, float* out) {
+  using namespace nmo;
+  Ctx c{};
+  c.T = T; c.O.OPT_SNF = opt_snf;
+  CANWATER(c, VEGTYP, in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], in[8], in[9], 1, in[10], in[11],
+           in[12] != 0.f, io[0], io[1], io[2], out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);
+}
+// SNOWWATER: sc = {DT SFCTMP SNOWHIN QSNOW QSNFRO QSNSUB QRAIN}; arrays in the oracle's Fortran bounds packed from the
+// lowest index; io scalars = {SNOWH SNEQV}; out = {QSNBOT SNOFLOW PONDING1 PONDING2}
+void nmo_snowwater(const int* IMELT7, const float* sc, const float* ZSOIL4, const float* FICEOLD3, int* ISNOW, float* io2,
+                   float* SNICE3, float* SNLIQ3, float* SH2O4, float* SICE4, float* STC7, float* ZSNSO7, float* DZSNSO7,
+                   float* out4) {
+  using namespace nmo;
+  IA<-NSNOW + 1, NSOIL> im;
+  ASoil zs, sh, si; ASnow fo, ice, liq; ASnSo stc, zsn, dz;
+  for (int k = -2; k <= NSOIL; ++k) { im(k) = IMELT7[k + 2]; stc(k) = STC7[k + 2]; zsn(k) = ZSNSO7[k + 2]; dz(k) = DZSNSO7[k + 2]; }
+  for (int k = 1; k <= NSOIL; ++k) { zs(k) = ZSOIL4[k - 1]; sh(k) = SH2O4[k - 1]; si(k) = SICE4[k - 1]; }
+  for (int k = -2; k <= 0; ++k) { fo(k) = FICEOLD3[k + 2]; ice(k) = SNICE3[k + 2]; liq(k) = SNLIQ3[k + 2]; }
+  SNOWWATER(im, sc[0], zs, sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], fo, *ISNOW, io2[0], io2[1], ice, liq, sh, si, stc,
+            zsn, dz, out4[0], out4[1], out4[2], out4[3]);
+  for (int k = -2; k <= NSOIL; ++k) { STC7[k + 2] = stc(k); ZSNSO7[k + 2] = zsn(k); DZSNSO7[k + 2] = dz(k); }
+  for (int k = 1; k <= NSOIL; ++k) { SH2O4[k - 1] = sh(k); SICE4[k - 1] = si(k); }
+  for (int k = -2; k <= 0; ++k) { SNICE3[k + 2] = ice(k); SNLIQ3[k + 2] = liq(k); }
+}
+// SOILWATER for one soil type: sc = {DT QINSUR QSEVA}; io = {ZWT SMCWTD DEEPRECH}; out = {RUNSRF QDRAIN RUNSUB FCRMAX}
+int nmo_soilwater(const noahmp_tables* T, int opt_run, int opt_inf, int SOILTYP, const float* sc, const float* ZSOIL4,
+                  const float* ETRANI4, const float* SICE4, float* SH2O4, float* SMC4, float* io3, float* out4) {
+  using namespace nmo;
+  Ctx c{};
+  c.T = T; c.O.OPT_RUN = opt_run; c.O.OPT_INF = opt_inf;
+  ASoil zs, et, si, sh, smc, wcnd;
+  for (int k = 1; k <= NSOIL; ++k) { zs(k) = ZSOIL4[k - 1]; et(k) = ETRANI4[k - 1]; si(k) = SICE4[k - 1]; sh(k) = SH2O4[k - 1]; smc(k) = SMC4[k - 1]; }
+  if (REDPRM(c, 7, SOILTYP, 1, zs, 1)) return 1;
+  ASnSo dz; dz.fill(0.f);
+  dz(1) = -zs(1);
+  for (int k = 2; k <= NSOIL; ++k) dz(k) = zs(k - 1) - zs(k);
+  out4[2] = 0.f;  // RUNSUB: the caller's zero survives for opt_run 3/4/5
+  SOILWATER(c, sc[0], zs, dz, sc[1], sc[2], et, si, sh, smc, io3[0], 1, 7, io3[1], io3[2], out4[0], out4[1], out4[2], wcnd,
+            out4[3]);
+  for (int k = 1; k <= NSOIL; ++k) { SH2O4[k - 1] = sh(k); SMC4[k - 1] = smc(k); }
+  return 0;
+}
+// CO2FLUX: sc = {IGS DT STC1 PSN TV WROOT WSTRES FOLN LAPM}; pools = {XLAI XSAI LFMASS RTMASS STMASS FASTCP STBLCP WOOD};
+// out = {GPP NPP NEE AUTORS HETERS TOTSC TOTLB}
+void nmo_co2flux(const noahmp_tables* T, int VEGTYP, const float* sc, float* pools, float* out7) {
+  using namespace nmo;
+  Ctx c{};
+  c.T = T;
+  ASnSo stc; stc.fill(0.f);
+  stc(1) = sc[2];
+  CO2FLUX(c, VEGTYP, sc[0], sc[1], stc, sc[3], sc[4], sc[5], sc[6], sc[7], sc[8], pools[0], pools[1], pools[2], pools[3],
+          pools[4], pools[5], pools[6], pools[7], out7[0], out7[1], out7[2], out7[3], out7[4], out7[5], out7[6]);
+}
+}
+

@@ -26,27 +26,41 @@ def lits(text, fortran):
             if n is not None and n not in ("0", "1", "2", "3", "4", "5", "6", "7"):
                 out[n] += 1
     return out
-fr = {}
-for f in F:
-    txt = open(f, errors="ignore").read()
-    for m in re.finditer(r"^\s*SUBROUTINE\s+(\w+).*?^\s*END\s+SUBROUTINE\s+\1", txt, flags=re.S | re.M | re.I):
-        fr[m.group(1).upper()] = lits(m.group(0), True)
-cr = {}
-for f in C:
-    txt = open(f).read()
-    # crude function splitter: 'name(' at column 0..n followed by body until a line that is just '}'
-    for m in re.finditer(r"^(?:static\s+)?(?:inline\s+)?(?:void|int|float)\s+(\w+)\s*\([^;{]*\)\s*\{.*?^\}", txt, flags=re.S | re.M):
-        cr.setdefault(m.group(1).upper(), collections.Counter()).update(lits(m.group(0), False))
-alias = {"WTABLE_MMF_NOAHMP": "WTABLE"}
-for name in sorted(fr):
-    c = cr.get(alias.get(name, name))
-    if c is None:
-        base = name.replace("_GLACIER", "")
-        c = cr.get(base)
+def audit(repo="."):
+    """{routine: (sorted fortran-only literals, sorted oracle-only literals)} for the routines that differ, and the
+    list of reference routines without an oracle function of the same name."""
+    import os
+    fr = {}
+    for f in F:
+        txt = open(f, errors="ignore").read()
+        for m in re.finditer(r"^\s*SUBROUTINE\s+(\w+).*?^\s*END\s+SUBROUTINE\s+\1", txt, flags=re.S | re.M | re.I):
+            fr[m.group(1).upper()] = lits(m.group(0), True)
+    cr = {}
+    for f in C:
+        txt = open(os.path.join(repo, f)).read()
+        # crude function splitter: 'name(' at column 0..n followed by body until a line that is just '}'
+        for m in re.finditer(r"^(?:static\s+)?(?:inline\s+)?(?:void|int|float)\s+(\w+)\s*\([^;{]*\)\s*\{(?:[^\n]*\}[ \t]*$|.*?^\})", txt, flags=re.S | re.M):
+            cr.setdefault(m.group(1).upper(), collections.Counter()).update(lits(m.group(0), False))
+    alias = {"WTABLE_MMF_NOAHMP": "WTABLE"}
+    diff, missing = {}, []
+    for name in sorted(fr):
+        c = cr.get(alias.get(name, name))
         if c is None:
-            print(f"-- {name}: no oracle function of that name"); continue
-    a = fr[name]
-    only_f = {k: v for k, v in a.items() if k not in c}
-    only_c = {k: v for k, v in c.items() if k not in a}
-    if only_f or only_c:
-        print(f"{name}: fortran-only {sorted(only_f)}  oracle-only {sorted(only_c)}")
+            c = cr.get(name.replace("_GLACIER", ""))
+            if c is None:
+                missing.append(name)
+                continue
+        a = fr[name]
+        only_f = sorted(k for k in a if k not in c)
+        only_c = sorted(k for k in c if k not in a)
+        if only_f or only_c:
+            diff[name] = (only_f, only_c)
+    return diff, missing
+
+
+if __name__ == "__main__":
+    diff, missing = audit()
+    for name in missing:
+        print(f"-- {name}: no oracle function of that name")
+    for name, (f_, c_) in diff.items():
+        print(f"{name}: fortran-only {f_}  oracle-only {c_}")
