@@ -224,8 +224,8 @@ int noahmp_b200_set_forcing_hints(noahmp_b200_ctx* ctx, unsigned hints);
 /* Release the page-lock the library holds on one caller array (before the caller frees it). */
 int noahmp_b200_unpin(noahmp_b200_ctx* ctx, const void* host_array);
 /* RESIDENT mode runs as a pipeline over `nchunks` row chunks (forcing upload | physics | result download overlap);
- * 0 = automatic: one chunk below 2^20 cells, else about one per 2^21 cells, 3 to 9, the first and the last half as
- * tall as the others from 4 chunks on.  After the first re-binning the chunking is fixed: other counts than the
+ * 0 = automatic: one chunk below 2^20 cells, 5 below 2^21, else 9; the first and the last chunk are half as tall as the
+ * others from 4 chunks on.  After the first re-binning the chunking is fixed: other counts than the
  * binned one and 1 fall back to it. */
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
 /* Divergence control (north_star item 4): in RESIDENT mode the land columns are physically re-ordered every

@@ -452,15 +452,26 @@ struct SfcState {  // variables VEGE_FLUX / BARE_FLUX keep alive across SFCDIF c
   int MOZSGN;
 };
 
+// The four logarithms of SFCDIF1 (:4127-4130) depend only on the geometry, which is fixed during the canopy / ground
+// Newton iterations: the callers evaluate them once per column instead of once per pass (same expressions, same bits).
+struct SfcLogs {
+  float TMPCM, TMPCH, TMPCM2, TMPCH2;
+};
+NMP_DEV SfcLogs sfcdif1_logs(float ZLVL, float ZPD, float Z0M, float Z0H) {
+  SfcLogs g;
+  g.TMPCM = LOG((ZLVL - ZPD) / Z0M);
+  g.TMPCH = LOG((ZLVL - ZPD) / Z0H);
+  g.TMPCM2 = LOG((2.0f + Z0M) / Z0M);
+  g.TMPCH2 = LOG((2.0f + Z0H) / Z0H);
+  return g;
+}
+
 // noahmplsm.F90:4061-4220 (maths identical in glacier.F90:1202-1358)
 NMP_DEV void SFCDIF1(Ctx& c, int ITER, float SFCTMP, float RHOAIR, float H, float QAIR, float ZLVL, float ZPD,
-                     float Z0M, float Z0H, float UR, float MPE, SfcState& s, float& CM, float& CH) {
+                     float Z0M, float Z0H, float UR, float MPE, const SfcLogs& G, SfcState& s, float& CM, float& CH) {
   float MOZOLD = s.MOZ;
   if (ZLVL <= ZPD) c.fatal(NOAHMP_ERR_ZLVL, ZLVL - ZPD);
-  float TMPCM = LOG((ZLVL - ZPD) / Z0M);
-  float TMPCH = LOG((ZLVL - ZPD) / Z0H);
-  float TMPCM2 = LOG((2.0f + Z0M) / Z0M);
-  float TMPCH2 = LOG((2.0f + Z0H) / Z0H);
+  const float TMPCM = G.TMPCM, TMPCH = G.TMPCH, TMPCM2 = G.TMPCM2, TMPCH2 = G.TMPCH2;
   float MOZ2;
   if (ITER == 1) {
     s.FV = 0.0f; s.MOZ = 0.0f; MOZ2 = 0.0f;
@@ -635,9 +646,35 @@ NMP_DEV void STOMATA(const Ctx& c, int VEGTYP, float MPE, float APAR, float FOLN
   float RLB = RB / CF;
   float CIHI = 1.5f * CO2;
   float CILOW = 0.0f;
+#if NMP_FASTMATH
+  // production build: the loop-invariant quotients of CI2CI are formed once (five reciprocals per bisection step
+  // instead of seven; the parity build below keeps the reference's expression order)
+  const float WE0 = 0.5f * VCMX * c3, WE1 = 4000.0f * VCMX / SFCPRS * (1.f - c3);
+  const float J1 = J * (1.f - c3), V1 = VCMX * (1.f - c3), EAEI = EA / EI, MPP = mp * SFCPRS;
+  const float K137 = 1.37f * RLB * SFCPRS, K165 = SFCPRS * 1.65f;
+#endif
   for (int ITER = 1; ITER <= 20; ++ITER) {
     float CI = 0.5f * (CIHI + CILOW);
     // CI2CI (:5430-5463)
+#if NMP_FASTMATH
+    const float CICP = MAX(CI - CP, 0.0f);
+    float WJ = CICP * J / (CI + 2.0f * CP) * c3 + J1;
+    float WC = CICP * VCMX / (CI + AWC) * c3 + V1;
+    float WE = WE0 + WE1 * CI;
+    PSN = MIN(MIN(WJ, WC), WE) * IGS;
+    float CS = MAX(CO2 - K137 * PSN, MPE);
+    const float TQ = MPP * PSN / CS;
+    float A = TQ * EAEI + bp;
+    float B = (TQ + bp) * RLB - 1.f;
+    float C = -RLB;
+    float Q;
+    if (B >= 0.0f) Q = -0.5f * (B + SQRT(B * B - 4.0f * A * C));
+    else Q = -0.5f * (B - SQRT(B * B - 4.0f * A * C));
+    float R1 = Q / A;
+    float R2 = C / Q;
+    RS = MAX(R1, R2);
+    float FCI = MAX(CS - PSN * K165 * RS, 0.0f);
+#else
     float WJ = MAX(CI - CP, 0.0f) * J / (CI + 2.0f * CP) * c3 + J * (1.f - c3);
     float WC = MAX(CI - CP, 0.0f) * VCMX / (CI + AWC) * c3 + VCMX * (1.f - c3);
     float WE = 0.5f * VCMX * c3 + 4000.0f * VCMX * CI / SFCPRS * (1.f - c3);
@@ -653,6 +690,7 @@ NMP_DEV void STOMATA(const Ctx& c, int VEGTYP, float MPE, float APAR, float FOLN
     float R2 = C / Q;
     RS = MAX(R1, R2);
     float FCI = MAX(CS - PSN * SFCPRS * 1.65f * RS, 0.0f);
+#endif
     if (((CIHI - CILOW) <= CIERR) || ABS(FCI - CI) <= MPE) break;
     else if (FCI > CI) CILOW = CI;
     else CIHI = CI;
@@ -734,9 +772,11 @@ NMP_DEV void VEGE_FLUX(Ctx& c, const FluxIn& in, float VAI, float GAMMAV, float 
   float CIR = (2.f - EMV * (1.f - EMG)) * EMV * SB;
 
   const float Z0H = Z0M, Z0HG = Z0MG;
+  SfcLogs G{};
+  if (sfc == 1) G = sfcdif1_logs(in.ZLVL, ZPD, Z0M, Z0H);
   int ITER;
   for (ITER = 1; ITER <= 20; ++ITER) {
-    if (sfc == 1) SFCDIF1(c, ITER, SFCTMP, RHOAIR, H, in.QAIR, in.ZLVL, ZPD, Z0M, Z0H, UR, MPE, s, CM, CH);
+    if (sfc == 1) SFCDIF1(c, ITER, SFCTMP, RHOAIR, H, in.QAIR, in.ZLVL, ZPD, Z0M, Z0H, UR, MPE, G, s, CM, CH);
     if (sfc == 2) {
       SFCDIF2(ITER, Z0M, TAH, in.THAIR, UR, c.P.CZIL, in.ZLVL, CM, CH, s.MOZ, s.WSTAR, s.FV);
       CH = CH / UR;
@@ -891,9 +931,11 @@ NMP_DEV void BARE_FLUX(Ctx& c, const FluxIn& in, float ZPD, float Z0M, float LAT
   float CIR = EMG * SB;
   float CGH = 2.f * in.DF_TOP / in.DZ_TOP;
 
+  SfcLogs G{};
+  if (sfc == 1) G = sfcdif1_logs(in.ZLVL, ZPD, Z0M, Z0H);
 #pragma unroll 1
   for (int ITER = 1; ITER <= 5; ++ITER) {
-    if (sfc == 1) SFCDIF1(c, ITER, SFCTMP, RHOAIR, H, in.QAIR, in.ZLVL, ZPD, Z0M, Z0H, UR, MPE, s, CM, CH);
+    if (sfc == 1) SFCDIF1(c, ITER, SFCTMP, RHOAIR, H, in.QAIR, in.ZLVL, ZPD, Z0M, Z0H, UR, MPE, G, s, CM, CH);
     if (sfc == 2) {
       SFCDIF2(ITER, Z0M, TGB, in.THAIR, UR, c.P.CZIL, in.ZLVL, CM, CH, s.MOZ, s.WSTAR, s.FV);
       CH = CH / UR;

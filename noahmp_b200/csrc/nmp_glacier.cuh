@@ -78,9 +78,10 @@ NMP_DEV void GLACIER_FLUX(Ctx& c, float EMG, float DF_TOP, float DZ_TOP, float S
   const float Z0H = Z0M;
   float CIR = EMG * SB;
   float CGH = 2.f * DF_TOP / DZ_TOP;
+  const SfcLogs G = sfcdif1_logs(ZLVL, ZPD, Z0M, Z0H);
 #pragma unroll 1
   for (int ITER = 1; ITER <= 5; ++ITER) {
-    SFCDIF1(c, ITER, SFCTMP, RHOAIR, H, QAIR, ZLVL, ZPD, Z0M, Z0H, UR, MPE, s, CM, CH);
+    SFCDIF1(c, ITER, SFCTMP, RHOAIR, H, QAIR, ZLVL, ZPD, Z0M, Z0H, UR, MPE, G, s, CM, CH);
     RAHB = MAX(1.f, 1.f / (CH * UR));
     float RAWB = RAHB;
     float T = TDC(TGB);

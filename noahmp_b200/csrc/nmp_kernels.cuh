@@ -374,6 +374,7 @@ void launch_pair(const StepParams& base, const nmpf::StepRange& r, cudaStream_t 
 // compile-time option sets: dveg crs btr run sfc frz inf rad alb snf tbot stc
 using OptDefault = OptSet<4, 1, 1, 1, 1, 1, 1, 3, 2, 1, 2, 1>;  // BASELINE configs C1/C2/C4
 using OptDynVeg = OptSet<2, 1, 1, 1, 1, 1, 1, 3, 2, 1, 2, 1>;   // C3: dveg=2 dynamic vegetation
+using OptDynVegMMF = OptSet<2, 1, 1, 5, 1, 1, 1, 3, 2, 1, 2, 1>;  // C5: C3 with the MMF groundwater scheme (opt_run=5)
 
 template <class O>
 bool matches(const int* opt) {
@@ -394,6 +395,7 @@ const char* launch_step(const StepParams& base, const nmpf::StepRange& r, cudaSt
   }
   if (matches<OptDefault>(base.opt)) { launch_pair<OptDefault>(base, r, stream, launches); return "default"; }
   if (matches<OptDynVeg>(base.opt)) { launch_pair<OptDynVeg>(base, r, stream, launches); return "dynveg"; }
+  if (matches<OptDynVegMMF>(base.opt)) { launch_pair<OptDynVegMMF>(base, r, stream, launches); return "dynveg_mmf"; }
 #endif
   launch_pair<OptRuntime>(base, r, stream, launches);
   return "runtime";

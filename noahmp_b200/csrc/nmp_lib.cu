@@ -848,14 +848,15 @@ static int chunk_row(const noahmp_b200_ctx* ctx, int c, int nchunks) {
   const int u = c <= 0 ? 0 : (c >= nchunks ? units : 2 * c - 1);
   return (int)((long long)ctx->nj * u / units);
 }
-// Automatic number of row chunks of the RESIDENT-mode pipeline: about one chunk per 2^21 cells, at least 3 and at
-// most 9 for tiles of 2^20 cells and more (17.7 M cells -> 9, 8.8 M -> 5, 2.2 M -> 3), one below that.  Every
-// chunk costs ~25 API calls on the host; a small tile in many chunks is bound by those, not by PCIe or the kernel.
+// Automatic number of row chunks of the RESIDENT-mode pipeline: 9 (the first and the last half as tall as the others)
+// from 2^21 cells, 5 from 2^20, one below.  What a chunk costs is ~20 asynchronous API calls (0.04 ms of host time,
+// enqueued ahead of the GPU); what it buys is a shorter fill and drain of the upload | physics | download pipeline: the
+// call ends one chunk's kernel + download after the last upload (profiles/r02_notes.md: 3 equal chunks on a 4.4 M-cell
+// tile end 1.5 ms after the last byte went up, 9 chunks 0.3 ms).
 static int auto_chunks(const noahmp_b200_ctx* ctx) {
   if (ctx->nchunks) return std::min(ctx->nchunks, ctx->nj);
   if (ctx->ncell < (1LL << 20)) return 1;
-  const int n = 1 + (int)(ctx->ncell >> 21);
-  return std::min(std::min(9, std::max(3, n)), ctx->nj);
+  return std::min(ctx->ncell >= (1LL << 21) ? 9 : 5, ctx->nj);
 }
 struct ChunkRanges {
   int n = 0;

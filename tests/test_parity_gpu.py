@@ -129,9 +129,13 @@ def test_specialised_kernels_equal_runtime_kernel(built, tables_usgs, monkeypatc
     reads the options at run time (compared in the PARITY build: with FMA contraction on, two instantiations of
     the same source need not round alike)."""
     import noahmp_b200
-    for name, variant in (("C2", "default"), ("C3", "dynveg")):
+    for name, variant in (("C2", "default"), ("C3", "dynveg"), ("C5", "dynveg_mmf")):
         cfg = _cfg(name, 96, 80)
         _, st, state0 = make_case(cfg, tables_usgs)
+        if name == "C5":  # state the MMF scheme needs
+            state0["smoiseq"][...] = 0.8 * state0["smois"]
+            state0["zwtxy"][...] = -3.0
+            state0["smcwtdxy"][...] = 0.3
         a, b = clone_state(state0), clone_state(state0)
         m1 = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY)
         run_gpu(m1, cfg, st, a, 6)
