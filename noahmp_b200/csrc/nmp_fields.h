@@ -63,9 +63,16 @@ constexpr int NPLANES = kSlots.slot[NFIELDS];
 // internal planes after the argument-list fields: [NPLANES] = VEGE_FLUX pass count of the previous step (a key of
 // the column re-binning), then the NSTATIC static inputs in compact order (so that re-binned columns still read
 // them with unit stride)
+// NMP_SPLIT=1 (experimental build, tools/build_split.sh): ENERGY and WATER as two kernels; the values that cross the cut
+// travel through NHANDOFF extra planes (written by the first kernel, read by the second, never re-binned).
+#ifndef NMP_SPLIT
+#define NMP_SPLIT 0
+#endif
 constexpr int PLANE_PREV_ITERS = NPLANES;
 constexpr int PLANE_STATIC0 = NPLANES + 1;
-constexpr int NPLANES_ALLOC = NPLANES + 1 + 7;
+constexpr int NHANDOFF = NMP_SPLIT ? 20 : 0;
+constexpr int PLANE_HANDOFF0 = NPLANES + 1 + 7;
+constexpr int NPLANES_ALLOC = NPLANES + 1 + 7 + NHANDOFF;
 template <int F>
 struct SlotOf {
   static constexpr int value = kSlots.slot[F];
@@ -78,7 +85,7 @@ enum ForcingId {
 };
 static_assert(NFORC == NOAHMP_NFORCING, "forcing plane count");
 enum StaticId { ST_IVGTYP = 0, ST_ISLTYP, ST_VEGMAX, ST_TMN, ST_XLATIN, ST_XLAND, ST_XICE, NSTATIC };
-static_assert(NPLANES_ALLOC == NPLANES + 1 + NSTATIC, "internal plane count");
+static_assert(NPLANES_ALLOC == NPLANES + 1 + NSTATIC + NHANDOFF, "internal plane count");
 
 // column classes (noahmpdrv.F90:426-441)
 enum ColClass { CL_WATER = 0, CL_LAND = 1, CL_GLACIER = 2, CL_SEAICE = 3 };

@@ -221,8 +221,14 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const StepParams& p) {
 }
 
 // ---- land columns: REDPRM + NOAHMP_SFLX (noahmpdrv.F90:449-547, :681-714) ---------------------------
-template <class O>
-__global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __grid_constant__ StepParams p) {
+#ifndef NMP_WATER_MINBLOCKS
+#define NMP_WATER_MINBLOCKS 3
+#endif
+// PART 0: the fused column program.  NMP_SPLIT build: PART 1 = ENERGY half (same launch bounds), PART 2 = WATER half
+// (3 blocks of 256 threads per SM: <= 85 registers).
+template <class O, int PART = 0>
+__global__ void __launch_bounds__(NMP_BLOCK, PART == 2 ? NMP_WATER_MINBLOCKS : NMP_MINBLOCKS)
+land_kernel(const __grid_constant__ StepParams p) {
   // Warps are aligned to 32-column (128-byte) boundaries of the planes whatever the first column of the launch is
   // (row chunks of the RESIDENT pipeline start anywhere): the launch is shifted down by first % 32 lanes.
   int t = blockIdx.x * blockDim.x + threadIdx.x - (p.first & 31);
@@ -247,8 +253,10 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   s.TV = io.ld(NMP_SLOT(tvxy));
   s.CANLIQ = io.ld(NMP_SLOT(canliqxy));
   s.CANICE = io.ld(NMP_SLOT(canicexy));
-  s.EAH = io.ld(NMP_SLOT(eahxy));
-  s.TAH = io.ld(NMP_SLOT(tahxy));
+  if (PART != 2) {
+    s.EAH = io.ld(NMP_SLOT(eahxy));
+    s.TAH = io.ld(NMP_SLOT(tahxy));
+  }
   s.FWET = io.ld(NMP_SLOT(fwetxy));
   s.WA = io.ld(NMP_SLOT(waxy));  // for BEG_WB; reloaded with the rest of the water-table state before WATER
   s.LAI = io.ld(NMP_SLOT(xlaixy));
@@ -291,10 +299,13 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MINBLOCKS) land_kernel(const __
   }
   // every OUT member is assigned by NOAHMP_SFLX before use except on the dveg error path
   s.PONDING = 0.f; s.PONDING1 = 0.f; s.PONDING2 = 0.f; s.QSNBOT = 0.f; s.FPICE = 0.f;
-  NOAHMP_SFLX<O>(c, s, io);
-  if (io.on && p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
-  io.sti(nmpf::PLANE_PREV_ITERS, s.VEGE_ITERS);  // key of the column re-binning (nmp_lib.cu: rebin)
-  if (live && c.err) report_error(p, io.cell, c.err, c.errv);
+  NOAHMP_SFLX<O, PART>(c, s, io);
+  if (PART != 2) {
+    if (io.on && p.vege_iters) p.vege_iters[io.cell] = s.VEGE_ITERS;
+    io.sti(nmpf::PLANE_PREV_ITERS, s.VEGE_ITERS);  // key of the column re-binning (nmp_lib.cu: rebin)
+  }
+  // (the WATER half of the split build does not report again what the ENERGY half reported for a rejected column)
+  if (live && c.err && !(PART == 2 && bad_index)) report_error(p, io.cell, c.err, c.errv);
 }
 
 // ---- glacier columns: NOAHMP_GLACIER + sentinel fills (noahmpdrv.F90:552-628) ------------------------
@@ -359,8 +370,14 @@ void launch_pair(const StepParams& base, const nmpf::StepRange& r, cudaStream_t 
     StepParams p = base;
     p.first = r.land_first;
     p.count = nland;
+#if NMP_SPLIT
+    land_kernel<O, 1><<<(nland + (r.land_first & 31) + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
+    land_kernel<O, 2><<<(nland + (r.land_first & 31) + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
+    *launches += 2;
+#else
     land_kernel<O><<<(nland + (r.land_first & 31) + NMP_BLOCK - 1) / NMP_BLOCK, NMP_BLOCK, 0, stream>>>(p);
     ++*launches;
+#endif
   }
   if (nglac > 0) {
     StepParams p = base;

@@ -971,7 +971,7 @@ static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
     for (int f = 0; f < NFIELDS; ++f)
       for (int k = 0; k < kFields[f].layers; ++k) kind[kSlots.slot[f] + k] = (unsigned char)kFields[f].kind;
     for (int pl = 0; pl < NPLANES_ALLOC; ++pl)
-      if (kind[pl] == NMP_K_INOUT) ctx->moved_planes.push_back(pl);
+      if (kind[pl] == NMP_K_INOUT && pl < PLANE_HANDOFF0) ctx->moved_planes.push_back(pl);
     size_t need = 0;
     int bits = 5;
     while ((1 << (bits - 5)) < 64) ++bits;

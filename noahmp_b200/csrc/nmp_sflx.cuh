@@ -468,8 +468,61 @@ NMP_DEV void store_energy_outputs(const ColumnIO& io, const Col& s) {
   for (int K = 1; K <= NSOIL; ++K) io.st(NMP_SLOT(tslb) + K - 1, s.STC(K));  // soil temperatures: final after ENERGY
 }
 
+// ---- ENERGY | WATER as two kernels (NMP_SPLIT build): what crosses the cut -----------------------------------------
+// PART 0 = the fused column program; PART 1 = ATM ... ENERGY and the scatter of everything ENERGY finalised, then the
+// hand-off; PART 2 = hand-off, WATER, CARBON, ERROR's water balance and the rest of the scatter.  The arithmetic of a
+// column is the same in both forms (the PARITY build of either is bit-identical to the oracle).
+enum { HO_FCEV = 0, HO_FCTR, HO_FGEV, HO_FVEG, HO_ELAI, HO_ESAI, HO_IGS, HO_BTRAN, HO_BTRANI0, HO_FLAGS = HO_BTRANI0 + 4,
+       HO_FICEOLD0, HO_PONDING = HO_FICEOLD0 + 3, HO_BEG_WB, HO_PSN, HO_Q2B, HO_COUNT };
+static_assert(HO_COUNT <= 20, "hand-off planes");
+NMP_DEV void store_handoff(const ColumnIO& io, const Col& s, const SflxLocal& L, int failed) {
+  const int H = nmpf::PLANE_HANDOFF0;
+  io.st(H + HO_FCEV, s.FCEV); io.st(H + HO_FCTR, s.FCTR); io.st(H + HO_FGEV, s.FGEV); io.st(H + HO_FVEG, s.FVEG);
+  io.st(H + HO_ELAI, L.ELAI); io.st(H + HO_ESAI, L.ESAI); io.st(H + HO_IGS, L.IGS); io.st(H + HO_BTRAN, L.BTRAN);
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) io.st(H + HO_BTRANI0 + K - 1, L.BTRANI(K));
+  int flags = (L.FROZEN_CANOPY ? 1 : 0) | (L.FROZEN_GROUND ? 2 : 0) | (failed ? 4 : 0);
+#pragma unroll
+  for (int K = -2; K <= NSOIL; ++K) flags |= (L.IMELT(K) & 3) << (4 + 2 * (K + 2));
+  io.sti(H + HO_FLAGS, flags);
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) io.st(H + HO_FICEOLD0 + K + 2, s.FICEOLD(K));
+  io.st(H + HO_PONDING, s.PONDING); io.st(H + HO_BEG_WB, L.BEG_WB); io.st(H + HO_PSN, s.PSN); io.st(H + HO_Q2B, s.Q2B);
+  // state ENERGY changed and WATER reads back through the ordinary planes
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) {
+    io.st(NMP_SLOT(tsnoxy) + K + 2, s.STC(K));
+    io.st(NMP_SLOT(snicexy) + K + 2, s.SNICE(K));
+    io.st(NMP_SLOT(snliqxy) + K + 2, s.SNLIQ(K));
+  }
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) {
+    io.st(NMP_SLOT(smois) + K - 1, s.SMC(K));
+    io.st(NMP_SLOT(sh2o) + K - 1, s.SH2O(K));
+  }
+  io.st(NMP_SLOT(snow), s.SNEQV); io.st(NMP_SLOT(snowh), s.SNOWH); io.st(NMP_SLOT(tvxy), s.TV);
+  io.st(NMP_SLOT(qsfc), s.QSFC); io.st(NMP_SLOT(xlaixy), s.LAI); io.st(NMP_SLOT(xsaixy), s.SAI);
+}
+NMP_DEV int load_handoff(const ColumnIO& io, Col& s, SflxLocal& L) {
+  const int H = nmpf::PLANE_HANDOFF0;
+  s.FCEV = io.ld(H + HO_FCEV); s.FCTR = io.ld(H + HO_FCTR); s.FGEV = io.ld(H + HO_FGEV); s.FVEG = io.ld(H + HO_FVEG);
+  L.ELAI = io.ld(H + HO_ELAI); L.ESAI = io.ld(H + HO_ESAI); L.IGS = io.ld(H + HO_IGS); L.BTRAN = io.ld(H + HO_BTRAN);
+#pragma unroll
+  for (int K = 1; K <= NSOIL; ++K) L.BTRANI(K) = io.ld(H + HO_BTRANI0 + K - 1);
+  const int flags = io.ldi(H + HO_FLAGS);
+  L.FROZEN_CANOPY = (flags & 1) != 0;
+  L.FROZEN_GROUND = (flags & 2) != 0;
+  L.LATHEAG = L.FROZEN_GROUND ? HSUB : HVAP;
+#pragma unroll
+  for (int K = -2; K <= NSOIL; ++K) L.IMELT(K) = (flags >> (4 + 2 * (K + 2))) & 3;
+#pragma unroll
+  for (int K = -2; K <= 0; ++K) s.FICEOLD(K) = io.ld(H + HO_FICEOLD0 + K + 2);
+  s.PONDING = io.ld(H + HO_PONDING); L.BEG_WB = io.ld(H + HO_BEG_WB); s.PSN = io.ld(H + HO_PSN); s.Q2B = io.ld(H + HO_Q2B);
+  return (flags & 4) != 0;
+}
+
 // noahmplsm.F90:518-947, with the dispatcher's scatter of the column (noahmpdrv.F90:713-835) folded in
-template <class O>
+template <class O, int PART = 0>
 NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
   const float DTX = io.p.dt;
   const noahmp_tables& T = *c.T;
@@ -491,6 +544,7 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
 
   // TROOT (:798-801) is computed by the reference but never used by PHENOLOGY's body.
 
+  if constexpr (PART != 2) {
   L.BEG_WB = s.CANLIQ + s.CANICE + s.SNEQV + s.WA;
 #pragma unroll
   for (int IZ = 1; IZ <= NSOIL; ++IZ) L.BEG_WB = L.BEG_WB + s.SMC(IZ) * L.DZSNSO(IZ) * 1000.f;
@@ -526,11 +580,18 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
   if (L.SWDOWN != 0.f) s.ALBEDO = s.FSR / L.SWDOWN; else s.ALBEDO = -999.9f;
   if (s.ALBEDO > -999.f) io.st(NMP_SLOT(albedo), s.ALBEDO);
   store_energy_outputs(io, s);
+  s.SNEQVO = s.SNEQV;
+  io.st(NMP_SLOT(sneqvoxy), s.SNEQVO);
+  }  // PART != 2
+  if constexpr (PART == 1) {
+    store_handoff(io, s, L, c.err != 0);
+    return;
+  }
+  int energy_failed = 0;
+  if constexpr (PART == 2) energy_failed = load_handoff(io, s, L);
 
 #pragma unroll
   for (int IZ = 1; IZ <= NSOIL; ++IZ) L.SICE(IZ) = MAX(0.0f, s.SMC(IZ) - s.SH2O(IZ));
-  s.SNEQVO = s.SNEQV;
-  io.st(NMP_SLOT(sneqvoxy), s.SNEQVO);
 
   // water-table state is first needed here (late load)
   s.ZWT = io.ld(NMP_SLOT(zwtxy));
@@ -571,7 +632,7 @@ NMP_DEV void NOAHMP_SFLX(Ctx& c, Col& s, const ColumnIO& io) {
 #pragma unroll
     for (int IZ = 1; IZ <= NSOIL; ++IZ) END_WB = END_WB + s.SMC(IZ) * L.DZSNSO(IZ) * 1000.f;
     s.ERRWAT = END_WB - L.BEG_WB - (s.PRCP - s.ECAN - s.ETRAN - s.EDIR - s.RUNSRF - s.RUNSUB) * s.DT;
-    if (ABS(s.ERRWAT) > 0.1f) c.fatal(NOAHMP_ERR_ERRWAT, s.ERRWAT);
+    if (ABS(s.ERRWAT) > 0.1f && !energy_failed) c.fatal(NOAHMP_ERR_ERRWAT, s.ERRWAT);
   }
 
   float QFX = s.ETRAN + s.ECAN + s.EDIR;
