@@ -237,3 +237,24 @@ def test_oracle_init_is_tile_independent(built, tables_usgs_struct):
         for n in INIT_OUT:
             if n in whole:
                 assert np.array_equal(part[n], whole[n][j0:j1]), n
+
+
+@pytest.mark.gpu
+def test_groundwater_init_rejects_missing_soil_type_without_touching_the_tables(built, tables_usgs):
+    """iopt_run=5 with a missing-field fill in ISLTYP (-9999): the reference stops in lsminit
+    (noahmpdrv.F90:1008-1021); here NOAHMP_ERR_ISLTYP comes back with that message, the second init kernel does not
+    index the soil tables with it, nothing is written back and the context stays usable."""
+    import noahmp_b200
+    cfg, st, frc1, A, sc = init_case("C2", 48, 32, iopt_run=5)
+    m = noahmp_b200.NoahMP(tables_usgs, cfg.ni, cfg.nj, device=0)
+    bad = clone(A)
+    bad["isltyp"][5, 7] = -9999
+    before = bad["tvxy"].copy()
+    with pytest.raises(noahmp_b200.NoahmpError) as e:
+        m.init(bad, sc)
+    assert e.value.code == 9 and "ISLTYP" in str(e.value)
+    assert np.array_equal(bad["tvxy"], before)
+    good = clone(A)
+    assert m.init(good, sc) == 1  # STEPWTD = max(nint(30*60/3600), 1): the context is still usable
+    assert not np.array_equal(good["tvxy"], before)
+    m.close()

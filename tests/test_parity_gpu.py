@@ -494,3 +494,52 @@ def test_gpu_state_matches_committed_fixture(built, tables_usgs):
         w = want[f"{name}_{ni}x{nj}_{steps}steps"]
         bad = [n for n in w if zlib.crc32(np.ascontiguousarray(state[n]).tobytes()) != w[n]]
         assert not bad, (name, bad)
+
+
+def test_groundwater_device_loop_bitexact(built, tables_usgs):
+    """The path bench.py --config C5 times: step_device + wtable_device enqueued on one caller stream, no host round
+    trip between them (RESIDENT mode, the specialised dveg=2 / opt_run=5 kernel), 10 steps incl. a re-binning; the state
+    and the groundwater fields equal the oracle's bit for bit."""
+    import noahmp_b200
+    import torch
+    from oracle import oracle as O
+    cfg = _cfg("C5", 80, 60)
+    cfg.water_frac, cfg.glacier_frac = 0.1, 0.05
+    _, st, state = make_case(cfg, tables_usgs)
+    wt, wsc = S.groundwater_fields(cfg, st, state)
+    ts = _capi.tables_from_dict(tables_usgs)
+    s_cpu, w_cpu = _clone_gw(state, wt)
+    s_gpu, w_gpu = _clone_gw(state, wt)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY, sync=noahmp_b200.SYNC_RESIDENT)
+    m.set_rebin(4)
+    xp = S.backend()
+    O.set_math_mode(1)
+    stream = torch.cuda.Stream()
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), s_gpu, 1)
+    m.upload(arr, sc)
+    dev = [torch.as_tensor(x, device="cuda") for x in m.device_forcing()]
+    order = ["coszin", "t3d", "qv3d", "u_phy", "v_phy", "swdown", "glw", "p8w3d", "p8w3d", "rainbl", "vegfra", "dz8w"]
+    for step in range(1, 11):
+        frc = S.forcing(xp, cfg, step, st)
+        a1, sc = S.args_from(cfg, st, frc, s_cpu, step)
+        e1, _ = O.noahmplsm(a1, sc, ts, nthreads=4)
+        assert e1.code == 0
+        O.wtable(w_cpu, wsc, ts)
+        a2, _ = S.args_from(cfg, st, frc, s_gpu, step)
+        with torch.cuda.stream(stream):
+            for k, n in enumerate(order):
+                h = a2[n]
+                dev[k].copy_(torch.from_numpy(np.ascontiguousarray(h[:, 1 if k == 8 else 0, :] if h.ndim == 3 else h)),
+                             non_blocking=False)
+        m.step_device(step, sc["yr"], sc["julian"], sc["dt"], stream.cuda_stream)
+        m.wtable_device(w_gpu, wsc, stream.cuda_stream)
+    stream.synchronize()
+    assert m.variant == "dynveg_mmf" and m.rebins >= 2
+    assert m.status().code == 0
+    m.sync_host(a2, sc)
+    m.wtable_sync_host(w_gpu, wsc)
+    rep = diff_report(s_cpu, s_gpu)
+    assert not rep, rep
+    for n in WT_FIELDS:
+        assert np.array_equal(w_cpu[n].view(np.int32), w_gpu[n].view(np.int32)), n
+    m.close()
