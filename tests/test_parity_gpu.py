@@ -77,6 +77,13 @@ def test_c2_tile_bitexact_240_steps(built, tables_usgs):
     _bitexact(_cfg("C2", 116, 112), tables_usgs, 240, check_at=(1, 120))
 
 
+@pytest.mark.parametrize("name,ni,nj", [("C3", 96, 64), ("C4", 120, 90)])
+def test_240_steps_bitexact_snow_carbon_glacier(built, tables_usgs, name, ni, nj):
+    """North-star horizon (240 hourly steps = 10 days) on the dynamic-vegetation / 3-layer-snow physics (C3) and on the
+    land + glacier + water population (C4): every word still equal to the oracle's, checked after 1, 120 and 240 steps."""
+    _bitexact(_cfg(name, ni, nj), tables_usgs, 240, check_at=(1, 120))
+
+
 def test_c3_dynveg_snow_bitexact(built, tables_usgs):
     """BASELINE config 2 physics (dveg=2, 3-layer snow) on a 192x160 tile, 48 steps."""
     s = _bitexact(_cfg("C3", 192, 160), tables_usgs, 48, check_at=(1,))
