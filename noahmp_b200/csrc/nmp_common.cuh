@@ -106,6 +106,14 @@ NMP_DEV float SQRT(float x) { return sqrtf(x); }
 NMP_DEV float DIV(float a, float b) { return a / b; }
 #endif
 
+// x**2. (a REAL exponent): a libm pow call in the reference's own gfortran configuration (no -O, so no folding to x*x;
+// the translated reference of oracle/ref pins this).  The production build multiplies: __powf has no negative bases.
+#if NMP_FASTMATH
+NMP_DEV float POWR2(float x) { return x * x; }
+#else
+NMP_DEV float POWR2(float x) { return POW(x, 2.0f); }
+#endif
+
 // x**n for integer n as libgcc's __powisf2 evaluates it (what gfortran emits for REAL**INTEGER)
 NMP_DEV float POW2(float x) { return x * x; }
 NMP_DEV float POW3(float x) { return x * (x * x); }

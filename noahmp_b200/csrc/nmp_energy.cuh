@@ -100,7 +100,7 @@ NMP_DEV void CSNOW(int ISNOW, const N3& SNICE, const N3& SNLIQ, const L7& DZSNSO
       SNLIQV(IZ) = MIN(EPORE(IZ), SNLIQ(IZ) / (DZSNSO(IZ) * DENH2O));
       float BDSNOI = (SNICE(IZ) + SNLIQ(IZ)) / DZSNSO(IZ);
       CVSNO(IZ) = CICE * SNICEV(IZ) + CWAT * SNLIQV(IZ);
-      TKSNO(IZ) = 3.2217E-6f * (BDSNOI * BDSNOI);
+      TKSNO(IZ) = 3.2217E-6f * POWR2(BDSNOI);
     }
   }
 }
@@ -714,7 +714,7 @@ NMP_DEV void CANRES(const Ctx& c, float PAR, float SFCTMP, float RCSOIL, float E
   float FF = 2.0f * PAR / P.RGL;
   float RCS = (FF + P.RSMIN / P.RSMAX) / (1.0f + FF);
   RCS = MAX(RCS, 0.0001f);
-  float RCT = 1.0f - 0.0016f * ((P.TOPT - SFCTMP) * (P.TOPT - SFCTMP));
+  float RCT = 1.0f - 0.0016f * POWR2(P.TOPT - SFCTMP);
   RCT = MAX(RCT, 0.0001f);
   float RCQ = 1.0f / (1.0f + P.HS * MAX(0.f, Q2SAT - Q2));
   RCQ = MAX(RCQ, 0.01f);
@@ -1120,7 +1120,7 @@ NMP_DEV float FRH2O(const Prm& P, float TKELV, float SMC, float SH2O) {
     while ((NLOG < 10) && (KCOUNT == 0)) {
       NLOG = NLOG + 1;
       float t1 = (1.f + CK * SWL);
-      float DF = LOG((P.PSISAT * GRAV / HFUS) * (t1 * t1) * POW(P.SMCMAX / (SMC - SWL), BX)) -
+      float DF = LOG((P.PSISAT * GRAV / HFUS) * POWR2(t1) * POW(P.SMCMAX / (SMC - SWL), BX)) -
                  LOG(-(TKELV - TFRZ) / TKELV);
       float DENOM = 2.f * CK / (1.f + CK * SWL) + BX / (SMC - SWL);
       float SWLK = SWL - DF / DENOM;

@@ -423,7 +423,7 @@ NMP_DEV void NOAHMP_GLACIER(Ctx& c, Col& g) {
     L7 DF, HCPCT, FACT;
 #pragma unroll
     for (int K = -2; K <= NSOIL; ++K) { DF(K) = 0.f; HCPCT(K) = 0.f; FACT(K) = 0.f; }
-    float UR = MAX(SQRT(g.UU * g.UU + g.VV * g.VV), 1.f);
+    float UR = MAX(SQRT(POWR2(g.UU) + POWR2(g.VV)), 1.f);
     float Z0MG = Z0SNO;
     float ZPD = g.SNOWH;
     float ZLVL = ZPD + g.ZLVL;

@@ -226,6 +226,31 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const StepParams& p) {
 #endif
 // PART 0: the fused column program.  NMP_SPLIT build: PART 1 = ENERGY half (same launch bounds), PART 2 = WATER half
 // (3 blocks of 256 threads per SM: <= 85 registers).
+// NMP_TILE_PREFETCH = d > 0: a block starts the HBM -> L2 transfer of the INOUT / static planes of the columns that
+// block (blockIdx + d) will load (d = the number of resident blocks: that block starts about when this one ends).
+#ifndef NMP_TILE_PREFETCH
+#define NMP_TILE_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_tile(const StepParams& p, int block) {
+  constexpr int NIN = NMP_SLOT(t2mvxy);            // planes [0, NIN) are the INOUT arrays
+  constexpr int NPF = NIN + 1 + nmpf::NSTATIC;     // + PREV_ITERS + compact static planes
+  constexpr int LINES = NMP_BLOCK / 32;            // 128-byte lines per plane and block
+  const long long c0 = (long long)p.first - (p.first & 31) + (long long)block * NMP_BLOCK;
+  if (c0 >= (long long)p.first + p.count) return;
+  for (int i = threadIdx.x; i < NPF * LINES; i += NMP_BLOCK) {
+    int pl = i / LINES, ln = i % LINES;
+    if (pl >= NIN) pl += nmpf::PLANE_PREV_ITERS - NIN;
+    long long col = c0 + ln * 32;
+    if (col < p.first) col = p.first;
+    if (col >= (long long)p.first + p.count) continue;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + (long long)pl * p.np + col));
+  }
+  if (threadIdx.x < LINES) {
+    long long col = c0 + threadIdx.x * 32;
+    if (col >= p.first && col < (long long)p.first + p.count) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cell + col));
+  }
+}
+
 template <class O, int PART = 0>
 __global__ void __launch_bounds__(NMP_BLOCK, PART == 2 ? NMP_WATER_MINBLOCKS : NMP_MINBLOCKS)
 land_kernel(const __grid_constant__ StepParams p) {
@@ -237,6 +262,9 @@ land_kernel(const __grid_constant__ StepParams p) {
   bool live = t >= 0 && t < p.count;
   if (!live) t = t < 0 ? 0 : p.count - 1;
   ColumnIO io(p, (long long)p.first + t, live);
+#if NMP_TILE_PREFETCH
+  prefetch_tile(p, blockIdx.x + NMP_TILE_PREFETCH);
+#endif
   Ctx c;
   init_ctx(c, p);
 #if NMP_SMEM_TABLES

@@ -169,7 +169,7 @@ NMP_DEV void ENERGY(Ctx& c, Col& s, SflxLocal& L) {
   float PSNSUN = 0.f, PSNSHA = 0.f;
   s.T2MV = 0.f; s.Q2V = 0.f; s.CHV = 0.f; s.CHLEAF = 0.f; s.CHUC = 0.f; s.CHV2 = 0.f;
 
-  float UR = MAX(SQRT(s.UU * s.UU + s.VV * s.VV), 1.f);
+  float UR = MAX(SQRT(POWR2(s.UU) + POWR2(s.VV)), 1.f);
   float VAI = L.ELAI + L.ESAI;
   const bool VEG = VAI > 0.f;
 

@@ -31,8 +31,13 @@ extern int g_math_mode;
 inline float EXP(float x)   { NMO_TICK(EXP); return g_math_mode ? nmpm::expf_(x)   : std::exp(x); }
 inline float LOG(float x)   { NMO_TICK(LOG); return g_math_mode ? nmpm::logf_(x)   : std::log(x); }
 inline float LOG10(float x) { NMO_TICK(LOG10); return g_math_mode ? nmpm::log10f_(x) : std::log10(x); }
-inline float POW(float x, float y) { NMO_TICK(POW); return g_math_mode ? nmpm::powf_(x, y) : std::pow(x, y); }
-inline double DPOW(double x, double y) { NMO_TICK(DPOW); return g_math_mode ? nmpm::pow_d(x, y) : std::pow(x, y); }
+// x**y with a REAL exponent is a libm call in the reference's own gfortran configuration (arch/makefile.in.*.gcc sets
+// no -O, so no pow(x, 2.0) -> x*x folding): the libm leg goes through out-of-line functions (nmo_driver.cpp) that the
+// compiler cannot fold at a call site with a constant exponent either
+float powf_libm(float x, float y);
+double pow_libm(double x, double y);
+inline float POW(float x, float y) { NMO_TICK(POW); return g_math_mode ? float(nmpm::powf_(x, y)) : float(powf_libm(x, y)); }
+inline double DPOW(double x, double y) { NMO_TICK(DPOW); return g_math_mode ? nmpm::pow_d(x, y) : pow_libm(x, y); }
 inline float ATAN(float x)  { NMO_TICK(ATAN); return g_math_mode ? nmpm::atanf_(x)  : std::atan(x); }
 inline float TAN(float x)   { NMO_TICK(TAN); return g_math_mode ? nmpm::tanf_(x)   : std::tan(x); }
 inline float COS(float x)   { NMO_TICK(COS); return g_math_mode ? nmpm::cosf_(x)   : std::cos(x); }

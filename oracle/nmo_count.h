@@ -12,6 +12,9 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -28,6 +31,13 @@ enum Op { ADD = 0, MUL, DIV, CMP, EXP, LOG, LOG10, POW, DPOW, SQRT, ATAN, TAN, C
 struct Counters { unsigned long long n[NOPS]; };
 extern thread_local Counters tl;
 inline void tick(Op o) { ++tl.n[o]; }
+// optional value trace (debugging aid of the reference pin, tools/ref_trace_diff.py): every arithmetic result with its
+// operands, and statement markers (op = -1, a = source line) where the translated reference emits them
+struct TraceRec { int op; unsigned a, b, r; };
+extern thread_local std::vector<TraceRec>* trace;
+inline unsigned fbits(float x) { unsigned u; std::memcpy(&u, &x, 4); return u; }
+inline void rec(Op o, float a, float b, float r) { if (trace) trace->push_back(TraceRec{(int)o, fbits(a), fbits(b), fbits(r)}); }
+inline void mark(int line) { if (trace) trace->push_back(TraceRec{-1, (unsigned)line, 0u, 0u}); }
 
 struct Real {
   float v;
@@ -41,24 +51,24 @@ struct Real {
   constexpr operator float() const { return v; }
   Real operator-() const { return Real(-v); }
   Real operator+() const { return *this; }
-  Real& operator+=(Real o) { tick(ADD); v += o.v; return *this; }
-  Real& operator-=(Real o) { tick(ADD); v -= o.v; return *this; }
-  Real& operator*=(Real o) { tick(MUL); v *= o.v; return *this; }
-  Real& operator/=(Real o) { tick(DIV); v /= o.v; return *this; }
+  Real& operator+=(Real o) { tick(ADD); float r = v + o.v; rec(ADD, v, o.v, r); v = r; return *this; }
+  Real& operator-=(Real o) { tick(ADD); float r = v - o.v; rec(ADD, v, -o.v, r); v = r; return *this; }
+  Real& operator*=(Real o) { tick(MUL); float r = v * o.v; rec(MUL, v, o.v, r); v = r; return *this; }
+  Real& operator/=(Real o) { tick(DIV); float r = v / o.v; rec(DIV, v, o.v, r); v = r; return *this; }
 };
 static_assert(std::is_trivially_copyable<Real>::value && sizeof(Real) == 4, "Real is a float");
 
 template <class T>
 using arith = typename std::enable_if<std::is_arithmetic<T>::value, int>::type;
 
-#define NMO_BINOP(op, cls)                                                                        \
-  inline Real operator op(Real a, Real b) { tick(cls); return Real(a.v op b.v); }                 \
-  template <class T, arith<T> = 0> inline Real operator op(Real a, T b) { tick(cls); return Real(a.v op (float)b); } \
-  template <class T, arith<T> = 0> inline Real operator op(T a, Real b) { tick(cls); return Real((float)a op b.v); }
-NMO_BINOP(+, ADD)
-NMO_BINOP(-, ADD)
-NMO_BINOP(*, MUL)
-NMO_BINOP(/, DIV)
+#define NMO_BINOP(op, cls, sgn)                                                                   \
+  inline Real operator op(Real a, Real b) { tick(cls); float r = a.v op b.v; rec(cls, a.v, sgn b.v, r); return Real(r); } \
+  template <class T, arith<T> = 0> inline Real operator op(Real a, T b) { return a op Real((float)b); } \
+  template <class T, arith<T> = 0> inline Real operator op(T a, Real b) { return Real((float)a) op b; }
+NMO_BINOP(+, ADD, +)
+NMO_BINOP(-, ADD, -)
+NMO_BINOP(*, MUL, +)
+NMO_BINOP(/, DIV, +)
 #undef NMO_BINOP
 #define NMO_CMPOP(op)                                                                             \
   inline bool operator op(Real a, Real b) { tick(CMP); return a.v op b.v; }                        \

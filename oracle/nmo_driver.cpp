@@ -322,6 +322,11 @@ static int noahmplsm(const noahmp_lsm_args& a, const noahmp_tables& T, noahmp_st
 
 }  // namespace nmo
 
+namespace nmo {
+__attribute__((noinline)) float powf_libm(float x, float y) { return std::pow(x, y); }
+__attribute__((noinline)) double pow_libm(double x, double y) { return std::pow(x, y); }
+}  // namespace nmo
+
 extern "C" {
 
 // math_mode: 0 = host libm (reference-like), 1 = portable nmp_math.h (bit-comparable with the GPU

@@ -320,7 +320,7 @@ static void ENERGY_GLACIER(Ctx& c, GlacIO& g, int ISNOW, float RHOAIR, float EAI
   ASnSo DF, HCPCT, FACT;
   DF.fill(0.f); HCPCT.fill(0.f); FACT.fill(0.f);
   ASnow SNICEV, SNLIQV, EPORE;
-  float UR = MAX(SQRT(g.UU * g.UU + g.VV * g.VV), 1.f);
+  float UR = MAX(SQRT(POW(g.UU, 2.f) + POW(g.VV, 2.f)), 1.f);  // UU**2. : a REAL exponent, libm pow (nmo.h)
   float Z0MG = Z0SNO;
   float ZPD = g.SNOWH;
   float ZLVL = ZPD + g.ZLVL;

@@ -169,7 +169,7 @@ void CSNOW(int ISNOW, const ASnow& SNICE, const ASnow& SNLIQ, const ASnSo& DZSNS
     BDSNOI(IZ) = (SNICE(IZ) + SNLIQ(IZ)) / DZSNSO(IZ);
     CVSNO(IZ) = CICE * SNICEV(IZ) + CWAT * SNLIQV(IZ);
   }
-  for (int IZ = ISNOW + 1; IZ <= 0; ++IZ) TKSNO(IZ) = 3.2217E-6f * (BDSNOI(IZ) * BDSNOI(IZ));
+  for (int IZ = ISNOW + 1; IZ <= 0; ++IZ) TKSNO(IZ) = 3.2217E-6f * POW(BDSNOI(IZ), 2.f);
 }
 
 // noahmplsm.F90:2014-2118
@@ -546,7 +546,7 @@ void ENERGY(Ctx& c, SflxIO& s, SflxLocal& L) {
   float PSNSUN = 0.f, PSNSHA = 0.f;
   s.T2MV = 0.f; s.Q2V = 0.f; s.CHV = 0.f; s.CHLEAF = 0.f; s.CHUC = 0.f; s.CHV2 = 0.f;
 
-  float UR = MAX(SQRT(s.UU * s.UU + s.VV * s.VV), 1.f);
+  float UR = MAX(SQRT(POW(s.UU, 2.f) + POW(s.VV, 2.f)), 1.f);  // UU**2. : a REAL exponent, libm pow (nmo.h)
   float VAI = L.ELAI + L.ESAI;
   bool VEG = false;
   if (VAI > 0.f) VEG = true;

@@ -298,7 +298,7 @@ static void CANRES(Ctx& c, float PAR, float SFCTMP, float RCSOIL, float EAH, flo
   float FF = 2.0f * PAR / P.RGL;
   RCS = (FF + P.RSMIN / P.RSMAX) / (1.0f + FF);
   RCS = MAX(RCS, 0.0001f);
-  RCT = 1.0f - 0.0016f * ((P.TOPT - SFCTMP) * (P.TOPT - SFCTMP));
+  RCT = 1.0f - 0.0016f * POW(P.TOPT - SFCTMP, 2.0f);
   RCT = MAX(RCT, 0.0001f);
   RCQ = 1.0f / (1.0f + P.HS * MAX(0.f, Q2SAT - Q2));
   RCQ = MAX(RCQ, 0.01f);
@@ -719,7 +719,7 @@ static void FRH2O(Ctx& c, float& FREE, float TKELV, float SMC, float SH2O) {
     while ((NLOG < 10) && (KCOUNT == 0)) {
       NLOG = NLOG + 1;
       float t1 = (1.f + CK * SWL);
-      float DF = LOG((P.PSISAT * GRAV / HFUS) * (t1 * t1) * POW(P.SMCMAX / (SMC - SWL), BX)) -
+      float DF = LOG((P.PSISAT * GRAV / HFUS) * POW(t1, 2.f) * POW(P.SMCMAX / (SMC - SWL), BX)) -
                  LOG(-(TKELV - TFRZ) / TKELV);
       float DENOM = 2.f * CK / (1.f + CK * SWL) + BX / (SMC - SWL);
       float SWLK = SWL - DF / DENOM;
