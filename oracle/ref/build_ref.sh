@@ -12,7 +12,8 @@ trap 'rm -rf "$T"' EXIT
 python ref/f90cxx.py "$T/ref_gen.cpp" $R/util/module_model_constants.F \
   $R/phys/module_sf_noahmplsm.F90:skip=READ_MP_VEG_PARAMETERS,SFCDIF3,SFCDIF4 \
   $R/phys/module_sf_noahmp_glacier.F90 \
-  $R/phys/module_sf_noahmpdrv.F90:only=NOAHMPLSM
+  $R/phys/module_sf_noahmp_groundwater.F90 \
+  $R/phys/module_sf_noahmpdrv.F90:only=NOAHMPLSM,NOAHMP_INIT,SNOW_INIT,GROUNDWATER_INIT,EQSMOISTURE:noop=READ_MP_VEG_PARAMETERS,SOIL_VEG_GEN_PARM
 [ -n "$KEEP_GENERATED" ] && mkdir -p "$KEEP_GENERATED" && cp "$T/ref_gen.cpp" "$KEEP_GENERATED/"
 CXXFLAGS="-std=gnu++17 -ffp-contract=off -fno-fast-math -fPIC -Iref"
 g++ $CXXFLAGS -O2 -shared "$T/ref_gen.cpp" ref/ref_shim.cpp -o _ref/libnoahmp_ref.so

@@ -286,10 +286,21 @@ class Parser:
            ".LE.": "<=", ".GT.": ">", ".GE.": ">="}
 
     def p_rel(self):
-        a = self.p_add()
+        a = self.p_concat()
         if self.peek()[1] in self.REL and self.peek()[0] in ("op", "dotop"):
             op = self.REL[self.next()[1]]
-            a = Bin(op, a, self.p_add())
+            a = Bin(op, a, self.p_concat())
+        return a
+
+    def p_concat(self):
+        a = self.p_add()
+        while self.peek() == ("op", "//"):
+            self.next()
+            b = self.p_add()
+            if isinstance(a, Str) and isinstance(b, Str):
+                a = Str(a.text[:-1] + b.text[1:])
+            else:
+                a = Bin("//", a, b)
         return a
 
     def p_add(self):
@@ -438,6 +449,7 @@ class Program:
         self.modules = {}
         self.all_subs = {}  # NAME -> Scope (module procedures, for call signatures)
         self.skipped = set()
+        self.noop = set()  # procedures whose calls are dropped (table readers: the harness fills the tables)
 
 
 TYPE_RE = re.compile(r"^(INTEGER|REAL|DOUBLE\s*PRECISION|LOGICAL|CHARACTER)\b")
@@ -1042,6 +1054,8 @@ class Emitter:
                 return "(!" + self.ex(e.a, sc, elem) + ")"
             return "(%s%s)" % (e.op, self.ex(e.a, sc, elem))
         if isinstance(e, Bin):
+            if e.op == "//":
+                return '""'
             a, b = self.ex(e.a, sc, elem), self.ex(e.b, sc, elem)
             if e.op == "**":
                 ta, tb = self.typeof(e.a, sc), self.typeof(e.b, sc)
@@ -1395,16 +1409,18 @@ class Emitter:
             if rest:
                 self.emit_where(mask, [rest], sc, ind)
                 return ind
-            stack.append(("where", mask, []))
+            stack.append(["where", mask, [], [], False])
             return ind
         if stack and stack[-1][0] == "where":
+            k = stack[-1]
             if re.match(r"^END\s*WHERE", st):
-                k = stack.pop()
-                self.emit_where(k[1], k[2], sc, ind)
+                stack.pop()
+                self.emit_where(k[1], k[2], sc, ind, k[3])
                 return ind
-            if re.match(r"^ELSE\s*WHERE", st):
-                raise SyntaxError("ELSEWHERE not supported")
-            stack[-1][2].append(st)
+            if re.match(r"^ELSE\s*WHERE$", st):
+                k[4] = True
+                return ind
+            (k[3] if k[4] else k[2]).append(st)
             return ind
         # CALL
         m = re.match(r"^CALL\s+([A-Z_]\w*)\s*(\(.*\))?$", st)
@@ -1423,6 +1439,9 @@ class Emitter:
                     if strs:
                         msg = self.ex(strs[-1], sc)
                 self.w(ind, "F_FATAL(%s);" % msg)
+                return ind
+            if name in self.prog.noop:
+                self.w(ind, "/* call %s dropped: the harness fills what it reads */;" % name.lower())
                 return ind
             callee, cq = self.find_sub(sc, name)
             if callee is None and name in self.prog.skipped:
@@ -1444,7 +1463,7 @@ class Emitter:
             return ind
         raise SyntaxError("statement not understood")
 
-    def emit_where(self, mask, stmts, sc, ind):
+    def emit_where(self, mask, stmts, sc, ind, else_stmts=()):
         me = parse_expr(mask)
         sh = self.shape_of(me, sc)
         self.uid += 1
@@ -1453,11 +1472,14 @@ class Emitter:
             self.w(ind, "for (int %s = 0; %s < %s; ++%s)" % (ks[d], ks[d], sh[d][1], ks[d]))
             ind += 1
         self.w(ind, "if (%s) {" % self.ex(me, sc, ks))
-        for s in stmts:
-            eq = find_assign_eq(s)
-            lhs, rhs = parse_expr(s[:eq].strip()), parse_expr(s[eq + 1:].strip())
-            rsh = self.shape_of(rhs, sc)
-            self.w(ind + 1, "%s = %s;" % (self.ex(lhs, sc, ks), self.ex(rhs, sc, ks if rsh else None)))
+        for branch, lst in ((0, stmts), (1, else_stmts)):
+            if branch and else_stmts:
+                self.w(ind, "} else {")
+            for s_ in lst:
+                eq = find_assign_eq(s_)
+                lhs, rhs = parse_expr(s_[:eq].strip()), parse_expr(s_[eq + 1:].strip())
+                rsh = self.shape_of(rhs, sc)
+                self.w(ind + 1, "%s = %s;" % (self.ex(lhs, sc, ks), self.ex(rhs, sc, ks if rsh else None)))
         self.w(ind, "}")
 
     def emit_data(self, sc, ind):
@@ -1742,6 +1764,8 @@ def main(argv):
                 skip = tuple(p[5:].upper().split(","))
             elif p.startswith("only="):
                 only = tuple(p[5:].upper().split(","))
+            elif p.startswith("noop="):
+                prog.noop.update(p[5:].upper().split(","))
         parse_file(prog, parts[0], skip, only)
     em = Emitter(prog)
     em.out.append(PRELUDE)

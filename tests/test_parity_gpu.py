@@ -96,6 +96,30 @@ def test_c4_glacier_water_bitexact(built, tables_usgs):
     assert np.isfinite(s["tsk"]).all()
 
 
+def test_reference_golden_vectors(built, tables_usgs):
+    """The CUDA PARITY build, called through the C-ABI, against vectors THE REFERENCE produced (its Fortran text
+    machine-translated and compiled, tests/golden/gen_reference_vectors.py; portable math): every word of every
+    INOUT / OUT array, with neither the oracle nor the reference in the loop."""
+    import noahmp_b200
+    from test_reference_pin import check_against_golden
+    models = []
+
+    def factory(name):
+        from test_reference_pin import _gen
+        _, ni, nj = _gen().CASES[name][:3]
+        m = _model(tables_usgs, (ni, nj), noahmp_b200.MATH_PARITY)
+        models.append(m)
+
+        def step(arr, sc):
+            status = m.noahmplsm(arr, sc)
+            assert status.code == 0, (name, status.code, status.i, status.j)
+        return step
+
+    assert check_against_golden(factory, tables_usgs) > 1000
+    for m in models:
+        m.close()
+
+
 @pytest.mark.parametrize("opts", [
     dict(idveg=1, iopt_crs=2, iopt_btr=2, iopt_run=2, iopt_sfc=2, iopt_frz=2, iopt_inf=2, iopt_rad=1, iopt_alb=1,
          iopt_snf=2, iopt_tbot=1, iopt_stc=2),

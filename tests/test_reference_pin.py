@@ -1,0 +1,213 @@
+"""The pin of the oracle: the reference's own Fortran text, machine-translated to C++ (oracle/ref/f90cxx.py — a
+translator of the language, it knows no physics) and compiled into oracle/_ref/libnoahmp_ref.so, against the
+hand-written oracle, bit for bit, through the whole `noahmplsm` call (dispatcher, REDPRM, NOAHMP_SFLX, NOAHMP_GLACIER).
+
+Two layers:
+  * where the translated library exists (this container builds it from /root/reference; it travels to the GPU box as a
+    built .so): oracle == translated reference on C1..C4 populations, snow / glacier / sea-ice / water cells, every
+    accepted opt_* value, both math back ends (host libm and the portable nmp_math.h);
+  * everywhere: the committed golden vectors the translated reference produced (tests/golden/reference_vectors.npz,
+    made by tests/golden/gen_reference_vectors.py) are reproduced by the oracle — and by the CUDA PARITY build in
+    tests/test_parity_gpu.py::test_reference_golden_vectors — without the reference in the loop.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from noahmp_b200 import _capi, synthetic as S
+
+from helpers import clone_state, diff_report, make_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("gen_reference_vectors",
+                                                  os.path.join(ROOT, "tests", "golden", "gen_reference_vectors.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def R(built, tables_usgs_struct):
+    from oracle.ref import refmodel
+    so = refmodel.build()
+    if so is None:
+        pytest.skip("oracle/_ref/libnoahmp_ref.so is not built and there is no reference tree to build it from")
+    r = refmodel.RefModel(so)
+    missing, done = r.set_tables(tables_usgs_struct)
+    # every table the physics reads has a module variable of the same name in the reference
+    assert missing == ["nveg", "isurban_mp"], missing
+    return r
+
+
+def _both(O, R, cfg, tables, ts, nsteps, mode, prepare=None, skip=()):
+    """oracle and translated reference side by side, each advancing its own state; -> final oracle state"""
+    xp, st, state0 = make_case(cfg, tables)
+    if prepare:
+        prepare(state0)
+    sa, sb = clone_state(state0), clone_state(state0)
+    O.set_math_mode(mode)
+    R.set_math_mode(mode)
+    names = [n for n in _capi.INOUT_NAMES + _capi.OUT_NAMES if n not in skip]
+    for step in range(1, nsteps + 1):
+        frc = S.forcing(xp, cfg, step, st)
+        arr, sc = S.args_from(cfg, st, frc, sa, step)
+        status, _ = O.noahmplsm(arr, sc, ts, nthreads=4)
+        assert status.code == 0, (step, status.code, status.i, status.j, status.value)
+        arr2, sc2 = S.args_from(cfg, st, frc, sb, step)
+        R.noahmplsm(arr2, sc2)
+        rep = diff_report(sa, sb, names)
+        assert not rep, "step %d: %r" % (step, rep)
+    return st, sa
+
+
+def _cfg(name, ni, nj, **opts):
+    cfg = S.named_config(name)
+    cfg.ni, cfg.nj = ni, nj
+    cfg.opts.update(opts)
+    return cfg
+
+
+def test_the_translation_has_the_reference_argument_list(R):
+    """`noahmplsm` as translated takes exactly the members of noahmp_lsm_args, in order (the boundary, once more),
+    and the translated files hold the whole path."""
+    sig = R.signature("NOAHMPLSM")
+    assert [n for n, _ in sig] == [n.upper() for n, _ in _capi.NoahmpLsmArgs._fields_]
+    for name in ("NOAHMP_SFLX", "NOAHMP_GLACIER", "REDPRM", "ENERGY", "WATER", "CARBON", "VEGE_FLUX", "BARE_FLUX",
+                 "SFCDIF1", "SFCDIF2", "STOMATA", "CANRES", "TSNOSOI", "PHASECHANGE", "SNOWWATER", "SOILWATER",
+                 "GROUNDWATER", "SHALLOWWATERTABLE", "CO2FLUX", "ENERGY_GLACIER", "WATER_GLACIER"):
+        assert R.signature(name), name
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["libm", "portable"])
+def test_c1_24_steps(O, R, tables_usgs, tables_usgs_struct, mode):
+    """BASELINE config 0 (the reference's own CPU-runnable case): a diurnal cycle, every word of every array."""
+    _both(O, R, _cfg("C1", 10, 10), tables_usgs, tables_usgs_struct, 24, mode)
+
+
+def test_c2_nldas_tile(O, R, tables_usgs, tables_usgs_struct):
+    """BASELINE config 1 population (default options, 10 % water) on a 116 x 112 tile, 24 steps."""
+    st, s = _both(O, R, _cfg("C2", 116, 112), tables_usgs, tables_usgs_struct, 24, 0)
+    assert (st["xland"] > 1.5).mean() > 0.03
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["libm", "portable"])
+def test_c3_dynamic_vegetation_and_snow(O, R, tables_usgs, tables_usgs_struct, mode):
+    """The headline physics (dveg = 2 carbon pools, 3-layer snow) on 96 x 64 columns, 18 steps; all snow-layer counts
+    occur."""
+    st, s = _both(O, R, _cfg("C3", 96, 64), tables_usgs, tables_usgs_struct, 18, mode)
+    assert set(np.unique(s["isnowxy"])) >= {-3, -2, -1, 0}
+
+
+def test_c4_glacier_seaice_water(O, R, tables_usgs, tables_usgs_struct):
+    """Land + land-ice (NOAHMP_GLACIER) + water; 120 x 90 columns, 12 steps."""
+    cfg = _cfg("C4", 120, 90)
+    cfg.glacier_frac, cfg.snow_frac, cfg.t_base = 0.2, 0.4, 268.0
+    st, s = _both(O, R, cfg, tables_usgs, tables_usgs_struct, 12, 0)
+    assert (st["ivgtyp"] == S.ISICE).sum() > 200 and (st["xland"] > 1.5).sum() > 1000
+
+
+OPTS = [
+    dict(idveg=1, iopt_crs=2, iopt_btr=2, iopt_run=2, iopt_sfc=2, iopt_frz=2, iopt_inf=2, iopt_rad=1, iopt_alb=1,
+         iopt_snf=2, iopt_tbot=1, iopt_stc=2),
+    dict(idveg=3, iopt_crs=1, iopt_btr=3, iopt_run=3, iopt_sfc=1, iopt_frz=1, iopt_inf=1, iopt_rad=2, iopt_alb=2,
+         iopt_snf=3, iopt_tbot=2, iopt_stc=1),
+    dict(idveg=5, iopt_crs=2, iopt_btr=1, iopt_run=4, iopt_sfc=2, iopt_frz=2, iopt_inf=1, iopt_rad=3, iopt_alb=1,
+         iopt_snf=1, iopt_tbot=2, iopt_stc=2),
+    dict(idveg=2, iopt_crs=1, iopt_btr=1, iopt_run=5, iopt_sfc=1, iopt_frz=1, iopt_inf=2, iopt_rad=3, iopt_alb=2,
+         iopt_snf=1, iopt_tbot=2, iopt_stc=1),
+    dict(idveg=4, iopt_crs=1, iopt_btr=2, iopt_run=1, iopt_sfc=1, iopt_frz=2, iopt_inf=2, iopt_rad=1, iopt_alb=1,
+         iopt_snf=2, iopt_tbot=1, iopt_stc=1),
+]
+
+
+@pytest.mark.parametrize("k", range(len(OPTS)))
+def test_every_accepted_option_value(O, R, tables_usgs, tables_usgs_struct, k):
+    """Each value of each opt_* switch the reference accepts offline appears in one of the combinations."""
+    opts = OPTS[k]
+    cfg = _cfg("C3", 64, 48, **opts)
+    cfg.glacier_frac = 0.1
+
+    def prepare(state0):
+        if opts["iopt_run"] == 5:  # state of the MMF scheme (NOAHMP_INIT's groundwater block)
+            state0["smoiseq"][...] = 0.8 * state0["smois"]
+            state0["zwtxy"][...] = -3.0
+            state0["smcwtdxy"][...] = 0.3
+
+    _both(O, R, cfg, tables_usgs, tables_usgs_struct, 8, k % 2, prepare)
+
+
+def test_option_values_are_all_covered():
+    seen = {}
+    for o in OPTS:
+        for n, v in o.items():
+            seen.setdefault(n, set()).add(v)
+    want = dict(idveg={1, 2, 3, 4, 5}, iopt_crs={1, 2}, iopt_btr={1, 2, 3}, iopt_run={1, 2, 3, 4, 5}, iopt_sfc={1, 2},
+                iopt_frz={1, 2}, iopt_inf={1, 2}, iopt_rad={1, 2, 3}, iopt_alb={1, 2}, iopt_snf={1, 2, 3},
+                iopt_tbot={1, 2}, iopt_stc={1, 2})
+    assert seen == want
+
+
+def test_rejected_inputs_stop_both(O, R, tables_usgs, tables_usgs_struct):
+    """A soil type beyond the table: the reference calls wrf_error_fatal in REDPRM, the oracle reports the column."""
+    cfg = _cfg("C1", 10, 10)
+    xp, st, state = make_case(cfg, tables_usgs)
+    st["isltyp"][3, 4] = 25
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), state, 1)
+    O.set_math_mode(0)
+    status, _ = O.noahmplsm(arr, sc, tables_usgs_struct, nthreads=1)
+    assert status.code != 0 and (status.i, status.j) == (5, 4)
+    arr2, sc2 = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), clone_state(state), 1)
+    with pytest.raises(RuntimeError, match="too many input soil types"):
+        R.noahmplsm(arr2, sc2)
+
+
+# ---- the committed vectors: no reference needed ----------------------------------------------------------------------
+
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+
+
+def check_against_golden(step_fn_factory, tables):
+    """run every golden case through step_fn and compare with the stored arrays; -> number of arrays compared"""
+    g, gen = golden(), _gen()
+    n = 0
+    for name in gen.CASES:
+        got = gen.run(name, tables, step_fn_factory(name))
+        for key, arr in got.items():
+            want = g[key]
+            same = (arr == want) | (np.isnan(arr) & np.isnan(want)) if arr.dtype.kind == "f" else (arr == want)
+            assert same.all(), "%s: %d of %d words differ" % (key, int((~same).sum()), same.size)
+            n += 1
+    assert n == len(g.files)
+    return n
+
+
+def test_oracle_reproduces_the_reference_vectors(O, tables_usgs, tables_usgs_struct):
+    """Vectors computed by the translated reference (portable math) == the oracle, on any machine."""
+    O.set_math_mode(1)
+
+    def factory(name):
+        def step(arr, sc):
+            status, _ = O.noahmplsm(arr, sc, tables_usgs_struct, nthreads=2)
+            assert status.code == 0
+        return step
+
+    assert check_against_golden(factory, tables_usgs) > 1000
+
+
+def test_vectors_are_current(R, tables_usgs):
+    """Where the translated reference can be run, the committed file is what it produces now."""
+    R.set_math_mode(1)
+    assert check_against_golden(lambda name: R.noahmplsm, tables_usgs) > 1000
