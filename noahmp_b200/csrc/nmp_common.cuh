@@ -125,8 +125,9 @@ NMP_DEV float POW5(float x) { float t = x * x; return x * (t * t); }
 NMP_DEV float MIN(float a, float b) { return fminf(a, b); }  // one FMNMX; differs from the select only for NaN
 NMP_DEV float MAX(float a, float b) { return fmaxf(a, b); }
 #else
-NMP_DEV float MIN(float a, float b) { return (b < a) ? b : a; }
-NMP_DEV float MAX(float a, float b) { return (b > a) ? b : a; }
+// gfortran's expansion (m = a; if (b .op. m || isnan(m)) m = b): a NaN first argument gives way to the second
+NMP_DEV float MIN(float a, float b) { return (b < a || a != a) ? b : a; }
+NMP_DEV float MAX(float a, float b) { return (b > a || a != a) ? b : a; }
 #endif
 NMP_DEV float ABS(float a) { return fabsf(a); }
 NMP_DEV float SIGN(float a, float b) { return (b >= 0.0f) ? fabsf(a) : -fabsf(a); }

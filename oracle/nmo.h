@@ -53,9 +53,16 @@ inline float POWI(float x, int m) {
   while (n >>= 1) { x = x * x; if (n & 1) y *= x; }
   return m < 0 ? 1.0f / y : y;
 }
-// Fortran MIN/MAX/SIGN semantics
-inline float MIN(float a, float b) { return (b < a) ? b : a; }
-inline float MAX(float a, float b) { return (b > a) ? b : a; }
+// Fortran MIN/MAX/SIGN semantics.  gfortran expands MAX(a, b) as  m = a; if (b > m || isnan(m)) m = b  (trans-intrinsic.c,
+// without -ffinite-math-only): a NaN first argument is replaced by the second -- GROUNDWATER_INIT relies on it when its
+// Newton iteration for the deep soil moisture diverges: MAX(SMC, 1.E-4) is then 1.E-4, not NaN.
+#ifdef NMO_OPCOUNT
+inline bool ISNAN_(nmo_count::true_float a) { return a != a; }  // not an operation of the algorithm: not counted
+#else
+inline bool ISNAN_(float a) { return a != a; }
+#endif
+inline float MIN(float a, float b) { return (b < a || ISNAN_(a)) ? b : a; }
+inline float MAX(float a, float b) { return (b > a || ISNAN_(a)) ? b : a; }
 inline float MIN3(float a, float b, float c) { return MIN(MIN(a, b), c); }
 inline int IMIN(int a, int b) { return b < a ? b : a; }
 inline int IMAX(int a, int b) { return b > a ? b : a; }

@@ -141,26 +141,58 @@ class RefModel:
             raise RuntimeError("%s: %s" % (name, msg.value.decode(errors="replace")))
         return [None if s is None else s.value for s in scalars]
 
-    def noahmplsm(self, arrays, scalars):
-        """the reference's `noahmplsm` (module_sf_noahmpdrv) on host arrays in the product's own layout; arrays are
-        updated in place"""
-        a = _capi.make_args(arrays, scalars)
-        sig = self.signature("NOAHMPLSM")
-        fields = [n for n, _ in _capi.NoahmpLsmArgs._fields_]
-        if [n.upper() for n in fields] != [n for n, _ in sig]:
-            raise RuntimeError("noahmp_lsm_args and the reference's dummy list differ: %r" %
-                               [(x, y) for x, y in zip([n.upper() for n in fields], [n for n, _ in sig]) if x != y][:5])
+    def call_struct(self, name, struct, extra=None, strict=True):
+        """call procedure `name` taking each dummy argument from the member of the same (lower-case) name of a ctypes
+        struct of the C-ABI (include/noahmp_b200.h), or from `extra`; a NULL pointer member = an absent OPTIONAL
+        argument.  strict: the struct's members must be the dummy list, in order (the drop-in boundary)."""
+        sig = self.signature(name)
+        fields = [n for n, _ in struct._fields_]
+        extra = extra or {}
+        if strict:
+            want = [n.lower() for n, _ in sig if n.lower() not in extra]
+            if fields != want:
+                raise RuntimeError("%s: the struct and the reference's dummy list differ: %r" %
+                                   (name, [(x, y) for x, y in zip(fields, want) if x != y][:5]))
         argv = (C.c_void_p * len(sig))()
         keep = []
-        for i, (n, (an, at)) in enumerate(zip(fields, sig)):
-            v = getattr(a, n)
-            if at[0].isupper():
-                argv[i] = C.cast(v, C.c_void_p).value
+        for i, (an, at) in enumerate(sig):
+            n = an.lower()
+            if n in extra:
+                v = extra[n]
             else:
-                c = _CT[at](v)
+                v = getattr(struct, n)
+            if at[0].isupper():
+                argv[i] = C.cast(v, C.c_void_p).value if not isinstance(v, np.ndarray) else v.ctypes.data
+            elif at == "c":
+                b = C.create_string_buffer(str(v).encode())
+                keep.append(b)
+                argv[i] = C.addressof(b)
+            else:
+                if isinstance(v, C._Pointer):  # scalar passed by address (INTENT(OUT))
+                    argv[i] = C.cast(v, C.c_void_p).value
+                    continue
+                c = _CT[at](bool(v) if at == "l" else v)
                 keep.append(c)
                 argv[i] = C.addressof(c)
         msg = C.create_string_buffer(512)
-        rc = self.lib.ref_call_NOAHMPLSM(argv, msg, 512)
+        rc = getattr(self.lib, "ref_call_" + name)(argv, msg, 512)
         if rc:
-            raise RuntimeError("noahmplsm: " + msg.value.decode(errors="replace"))
+            raise RuntimeError("%s: %s" % (name, msg.value.decode(errors="replace")))
+
+    def noahmplsm(self, arrays, scalars):
+        """the reference's `noahmplsm` (module_sf_noahmpdrv) on host arrays in the product's own layout; arrays are
+        updated in place"""
+        self.call_struct("NOAHMPLSM", _capi.make_args(arrays, scalars))
+
+    def init(self, arrays, scalars, mminlu="USGS"):
+        """the reference's NOAHMP_INIT (its table readers left out: set_tables() does their work)"""
+        arrays = dict(arrays)
+        step = np.zeros(1, np.int32)
+        if scalars.get("iopt_run") == 5:
+            arrays["stepwtd"] = step
+        self.call_struct("NOAHMP_INIT", _capi.make_init_args(arrays, scalars), extra={"mminlu": mminlu})
+        return int(step[0]) if scalars.get("iopt_run") == 5 else None
+
+    def wtable(self, arrays, scalars):
+        """the reference's WTABLE_mmf_noahmp (module_sf_noahmp_groundwater)"""
+        self.call_struct("WTABLE_MMF_NOAHMP", _capi.make_wtable_args(arrays, scalars))

@@ -1,6 +1,7 @@
 """The pin of the oracle: the reference's own Fortran text, machine-translated to C++ (oracle/ref/f90cxx.py — a
 translator of the language, it knows no physics) and compiled into oracle/_ref/libnoahmp_ref.so, against the
-hand-written oracle, bit for bit, through the whole `noahmplsm` call (dispatcher, REDPRM, NOAHMP_SFLX, NOAHMP_GLACIER).
+hand-written oracle, bit for bit, through the whole `noahmplsm` call (dispatcher, REDPRM, NOAHMP_SFLX, NOAHMP_GLACIER),
+NOAHMP_INIT (with GROUNDWATER_INIT) and WTABLE_mmf_noahmp.
 
 Two layers:
   * where the translated library exists (this container builds it from /root/reference; it travels to the GPU box as a
@@ -171,6 +172,57 @@ def test_rejected_inputs_stop_both(O, R, tables_usgs, tables_usgs_struct):
     arr2, sc2 = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), clone_state(state), 1)
     with pytest.raises(RuntimeError, match="too many input soil types"):
         R.noahmplsm(arr2, sc2)
+
+
+def _same(x, y):
+    return ((x == y) | (np.isnan(x) & np.isnan(y))).all() if x.dtype.kind == "f" else (x == y).all()
+
+
+@pytest.mark.parametrize("name,ni,nj,run", [("C4", 96, 64, 1), ("C3", 64, 48, 1), ("C2", 60, 44, 5), ("C3", 130, 70, 5)])
+def test_noahmp_init(O, R, tables_usgs_struct, name, ni, nj, run):
+    """NOAHMP_INIT (SNOW_INIT; with iopt_run = 5 also GROUNDWATER_INIT, EQSMOISTURE and LATERALFLOW) on raw cold-start
+    fields: every array it writes.  The groundwater cases contain columns whose Newton iteration for the deep soil
+    moisture diverges to NaN, which the reference's MAX(SMC, 1.E-4) turns into 1.E-4 (gfortran's MAX)."""
+    import test_init as TI
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        A, sc = TI.init_case(name, ni, nj, run)[3:]
+        B = TI.clone(A)
+        rc, step_o = O.init(A, sc, tables_usgs_struct)
+        step_r = R.init(B, sc)
+        assert rc == 0 and step_o == step_r
+        bad = [n for n in A if isinstance(A[n], np.ndarray) and not _same(A[n], B[n])]
+        assert not bad, (mode, bad)
+
+
+@pytest.mark.parametrize("name,ni,nj", [("C4", 40, 30), ("C3", 96, 64), ("C2", 80, 60)])
+def test_wtable_coupled_with_the_column_physics(O, R, tables_usgs, tables_usgs_struct, name, ni, nj):
+    """opt_run = 5: six steps of noahmplsm followed by WTABLE_mmf_noahmp (LATERALFLOW, UPDATEWTD), the oracle and the
+    translated reference each on its own state."""
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        cfg = _cfg(name, ni, nj, iopt_run=5)
+        xp, st, sa = make_case(cfg, tables_usgs)
+        sa["smoiseq"][...] = 0.8 * sa["smois"]
+        sa["zwtxy"][...] = -3.0
+        sa["smcwtdxy"][...] = 0.3
+        sb = clone_state(sa)
+        wa, wsc = S.groundwater_fields(cfg, st, sa)
+        wb, _ = S.groundwater_fields(cfg, st, sb)
+        for step in range(1, 7):
+            frc = S.forcing(xp, cfg, step, st)
+            arr, sc = S.args_from(cfg, st, frc, sa, step)
+            O.noahmplsm(arr, sc, tables_usgs_struct, nthreads=4)
+            arr2, sc2 = S.args_from(cfg, st, frc, sb, step)
+            R.noahmplsm(arr2, sc2)
+            O.wtable(wa, wsc, tables_usgs_struct)
+            R.wtable(wb, wsc)
+            bad = [n for n in wa if isinstance(wa[n], np.ndarray) and not _same(wa[n], wb[n])]
+            bad += ["state." + n for n in sa if not _same(sa[n], sb[n])]
+            assert not bad, (mode, step, bad)
+        assert np.abs(wa["qslat"]).max() > 0
 
 
 # ---- the committed vectors: no reference needed ----------------------------------------------------------------------
