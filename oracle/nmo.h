@@ -6,10 +6,14 @@
 //   phys/module_sf_noahmp_glacier.F90 :: NOAHMP_GLACIER (land-ice columns)
 // routine by routine, in source order, fp32 with the one fp64 temporary the reference has.
 //
-// PARITY UNPINNED: the reference ships no golden vectors for this path and no Fortran compiler
-// exists in the build image, so this restatement could not be checked against reference output.
-// It is pinned only by the model's own conservation checks (ERROR / ERROR_GLACIER) and by
-// micro known-answer tests (tests/test_oracle_*.py).
+// PARITY PINNED BY TRANSLATION: the reference ships no golden vectors for this path and the build image has no Fortran
+// compiler, so the reference's own Fortran text is machine-translated to C++ (oracle/ref/f90cxx.py, a translator of the
+// language), compiled into oracle/_ref/libnoahmp_ref.so and this restatement is held to it bit for bit
+// (tests/test_reference_pin.py: noahmplsm on C1..C4 populations and every accepted option value, NOAHMP_INIT,
+// WTABLE_mmf_noahmp, both math modes; vectors it produced are committed under tests/golden/).  It is not a Fortran
+// compiler's output: DESIGN.md section 5 says what the translation assumes (gfortran's unoptimised configuration, which
+// is the reference's own; its MIN/MAX expansion).  Also pinned by the model's conservation checks (ERROR /
+// ERROR_GLACIER) and by physics-derived known answers (tests/test_oracle_*.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library.

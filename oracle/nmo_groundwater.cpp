@@ -1,6 +1,6 @@
 // nmo_groundwater.cpp — ORACLE (test infrastructure): WTABLE_mmf_noahmp, LATERALFLOW, UPDATEWTD.
 // Restates phys/module_sf_noahmp_groundwater.F90:14-606 in source order, fp32.
-// PARITY UNPINNED (see nmo.h): no reference output exists to compare with.
+// Pinned bit for bit against the machine-translated reference (see nmo.h; tests/test_reference_pin.py::test_wtable_*).
 #include <vector>
 #include "nmo.h"
 

@@ -1,6 +1,7 @@
 // nmo_init.cpp — ORACLE (test infrastructure): the cold start NOAHMP_INIT with SNOW_INIT, GROUNDWATER_INIT and
 // EQSMOISTURE.  Restates phys/module_sf_noahmpdrv.F90:847-1522 in source order, fp32.
-// PARITY UNPINNED (see nmo.h): no reference output exists to compare with; cross-checked in tests/ against the
+// Pinned bit for bit against the machine-translated reference (see nmo.h; tests/test_reference_pin.py::test_noahmp_init);
+// also cross-checked in tests/ against the
 // independent numpy restatement of the same routines in noahmp_b200/synthetic.py.
 #include <cmath>
 #include <vector>

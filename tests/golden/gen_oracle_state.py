@@ -1,7 +1,7 @@
 """Regression fixture of the CPU oracle itself: CRC-32 of every INOUT/OUT array after 24 steps of configuration C1
 (10 x 10, the reference's own CPU-runnable case) and 6 steps of a 48 x 32 window of C4 (land / glacier / water mix),
-in the portable-math mode, whose arithmetic does not depend on the host libm.  NOT reference output (the reference
-cannot be run here): it pins the oracle against accidental change between rounds.
+in the portable-math mode, whose arithmetic does not depend on the host libm.  Not reference output (that is
+reference_vectors.npz, beside this file): it pins the oracle against accidental change between rounds.
 usage: python tests/golden/gen_oracle_state.py   (rewrites tests/golden/oracle_state.json)"""
 import json
 import os

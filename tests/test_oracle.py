@@ -1,6 +1,6 @@
 """The CPU oracle against everything that can pin it without the reference binary: analytic known
 answers, the model's own conservation checks on every synthetic configuration, and the portable math it shares
-with the GPU parity build.  The reference ships no golden vectors for this path: PARITY UNPINNED (oracle/nmo.h)."""
+with the GPU parity build.  (The pin against the reference's own text is tests/test_reference_pin.py.)"""
 import ctypes as C
 
 import numpy as np
