@@ -23,4 +23,6 @@ if [ "$1" = "trace" ]; then
   g++ $CXXFLAGS -O1 -include nmo_count.h -c ref/ref_shim.cpp -o "$T/ref_shim_count.o"
   g++ $CXXFLAGS -O1 -c nmo_count.cpp -o "$T/ref_count.o"
   g++ -shared "$T/ref_gen_count.o" "$T/ref_shim_count.o" "$T/ref_count.o" -o _ref/libnoahmp_ref_count.so
+  # statement-coverage instantiation: tools/ref_coverage.py
+  g++ $CXXFLAGS -O1 -DREF_COVERAGE -shared "$T/ref_gen.cpp" ref/ref_shim.cpp -o _ref/libnoahmp_ref_cov.so
 fi

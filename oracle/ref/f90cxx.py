@@ -827,6 +827,7 @@ class Emitter:
         self.uid = 0
         self.warnings = []
         self.files = []
+        self.markers = []  # (file id * 100000 + line, enclosing module procedure) of every executable statement
 
     # ---- name resolution -----------------------------------------------------------------------------------
     def module_public(self, mname, seen=None):
@@ -1264,7 +1265,8 @@ class Emitter:
                 if label is not None:
                     self.w(ind, "L%s: ;" % label)
                 if not re.match(r"^(ELSE|END|CASE)", st) and not (stack and stack[-1][0] == "where"):
-                    self.w(ind, "REF_LINE(%d);" % (self.file_id(sc) * 100000 + no))
+                    self.markers.append((self.file_id(sc) * 100000 + no, top_name(sc)))
+                    self.w(ind, "REF_LINE(%d);" % self.markers[-1][0])
                 ind = self.emit_stmt(st, sc, ind, stack)
             except (SyntaxError, NameError, TypeError, KeyError, AttributeError, IndexError) as e:
                 raise type(e)("%s:%d [%s] %s\n    statement: %s" % (getattr(sc, "path", "?"), no, sc.name, e, st))
@@ -1509,6 +1511,10 @@ class Emitter:
         return self.files.index(path)
 
     def emit_registry(self, order):
+        names = sorted(set(n for _, n in self.markers))
+        self.w(0, "static const int ref_marker_table[] = {%s};" % ", ".join("%d,%d" % (m, names.index(n)) for m, n in self.markers))
+        self.w(0, 'extern "C" const int* ref_markers(int* n) { *n = %d; return ref_marker_table; }' % len(self.markers))
+        self.w(0, 'extern "C" const char* ref_marker_names() { return "%s"; }' % ";".join(names))
         self.w(0, 'extern "C" const char* ref_files() { return "%s"; }' % ";".join(str(x) for x in self.files))
         """name -> storage table of the module variables, and an untyped entry point per module procedure"""
         self.w(0, "struct RefVar { const char* name; void* p; unsigned long bytes; char type; };")
@@ -1698,6 +1704,12 @@ _orig_split_decls = split_decls
 
 def split_decls(scope):  # noqa: F811  (idempotent wrapper)
     split_decls_once(scope)
+
+
+def top_name(sc):
+    while sc.parent is not None and sc.parent.kind != "module":
+        sc = sc.parent
+    return sc.name
 
 
 def find_assign_eq(st):

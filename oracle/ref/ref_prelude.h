@@ -21,8 +21,11 @@ extern int ref_math_mode;
 #endif
 
 // statement marker (source line of the Fortran statement): only the value-tracing build records it
-#ifdef NMO_OPCOUNT
+#if defined(NMO_OPCOUNT)
 #define REF_LINE(n) nmo_count::mark(n)
+#elif defined(REF_COVERAGE)
+extern unsigned char ref_cover[];  // statement coverage of the reference (tools/ref_coverage.py)
+#define REF_LINE(n) (ref_cover[n] = 1)
 #else
 #define REF_LINE(n) ((void)0)
 #endif

@@ -6,3 +6,7 @@ extern "C" int ref_get_math_mode(void) { return ref_math_mode; }
 // never inlined, so that a constant exponent at the call site is not folded (see ref_prelude.h)
 __attribute__((noinline)) float ref_powf(float x, float y) { return __builtin_powf(x, y); }
 __attribute__((noinline)) double ref_pow(double x, double y) { return __builtin_pow(x, y); }
+#ifdef REF_COVERAGE
+unsigned char ref_cover[1000000];
+extern "C" unsigned char* ref_cover_map(void) { return ref_cover; }
+#endif

@@ -52,9 +52,12 @@ def R(built, tables_usgs_struct):
     return r
 
 
-def _both(O, R, cfg, tables, ts, nsteps, mode, prepare=None, skip=()):
+def _both(O, R, cfg, tables, ts, nsteps, mode, prepare=None, skip=(), prepare_static=None):
     """oracle and translated reference side by side, each advancing its own state; -> final oracle state"""
     xp, st, state0 = make_case(cfg, tables)
+    if prepare_static:
+        prepare_static(st)
+        state0 = S.cold_start(cfg, st, S.forcing(xp, cfg, 1, st), tables)
     if prepare:
         prepare(state0)
     sa, sb = clone_state(state0), clone_state(state0)
@@ -149,6 +152,64 @@ def test_every_accepted_option_value(O, R, tables_usgs, tables_usgs_struct, k):
     _both(O, R, cfg, tables_usgs, tables_usgs_struct, 8, k % 2, prepare)
 
 
+# other climates than the configurations' own: (name, base, t_base, start, latitudes, snow_frac, glacier_frac, options)
+CLIMATES = [
+    ("tropical_july", "C2", 301.0, (2017, 7, 15, 0), (-10.0, 15.0), 0.0, 0.0, {}),
+    ("polar_winter", "C3", 243.0, (2017, 1, 10, 0), (60.0, 80.0), 0.9, 0.3, {}),
+    ("spring_melt", "C3", 272.5, (2017, 4, 10, 6), (40.0, 55.0), 0.8, 0.1, dict(iopt_alb=1, iopt_snf=3)),
+    ("summer_noon_dynveg", "C3", 295.0, (2017, 7, 1, 12), (30.0, 45.0), 0.0, 0.0, dict(iopt_rad=1, iopt_btr=2)),
+    ("autumn_frost_koren", "C2", 271.0, (2017, 10, 20, 18), (45.0, 60.0), 0.2, 0.05,
+     dict(iopt_frz=2, iopt_inf=2, iopt_stc=2, iopt_crs=2, iopt_run=3)),
+]
+
+
+@pytest.mark.parametrize("case", CLIMATES, ids=[c[0] for c in CLIMATES])
+def test_other_climates(O, R, tables_usgs, tables_usgs_struct, case):
+    """Branches the configurations' own winter / spring forcing does not reach: hot and humid, polar night, melting
+    snowpack, strong insolation on growing vegetation, freezing soil with the Koren99 options.  16 steps each."""
+    name, base, t_base, start, lat, snow, glac, opts = case
+    cfg = _cfg(base, 72, 48, **opts)
+    cfg.t_base, cfg.start, cfg.lat, cfg.snow_frac, cfg.glacier_frac = t_base, start, lat, snow, glac
+    _both(O, R, cfg, tables_usgs, tables_usgs_struct, 16, len(name) % 2)
+
+
+def test_long_melt_season(O, R, tables_usgs, tables_usgs_struct):
+    """Eight days of a melting snowpack: layers thin out, combine, vanish (COMBINE / DIVIDE / SNOWH2O's rarer branches,
+    PHASECHANGE's sign reversals), on vegetated and glacier columns."""
+    cfg = _cfg("C3", 48, 32, iopt_snf=3)
+    cfg.t_base, cfg.start, cfg.lat, cfg.snow_frac, cfg.glacier_frac = 278.0, (2017, 4, 20, 0), (38.0, 50.0), 0.9, 0.15
+    st, s = _both(O, R, cfg, tables_usgs, tables_usgs_struct, 192, 0)
+    assert (s["isnowxy"] == 0).mean() > 0.15 and set(np.unique(s["isnowxy"])) >= {-3, -2, -1, 0}
+
+
+def test_glacier_in_summer(O, R, tables_usgs, tables_usgs_struct):
+    """Land-ice columns whose upper layers cross the freezing point: the inter-layer heat / melt redistribution of
+    PHASECHANGE_GLACIER.  Leap year (YEARLEN = 366)."""
+    cfg = _cfg("C4", 40, 30)
+    cfg.t_base, cfg.start, cfg.lat, cfg.snow_frac, cfg.glacier_frac, cfg.water_frac = 276.5, (2016, 7, 5, 0), (60.0, 72.0), 0.3, 0.6, 0.1
+    _both(O, R, cfg, tables_usgs, tables_usgs_struct, 96, 1)
+
+
+def test_sea_ice_points_soil_type_14_and_dry_soil(O, R, tables_usgs, tables_usgs_struct):
+    """The dispatcher's special cases: sea-ice points (XICE >= XICE_THRES: skipped, SH2O = 1, LAI = 0.01, and the
+    ITIMESTEP = 1 fills), water-type soil at a land point (reset to 7), a bone-dry top layer (RSURF's guard); year 2000
+    (the 400-year leap rule)."""
+    cfg = _cfg("C2", 40, 30)
+    cfg.start = (2000, 2, 28, 12)
+
+    def prepare_static(st):
+        st["xice"][5:9, 3:30] = 1.0
+        st["isltyp"][12:15, 4:20] = 14
+
+    def prepare(state0):
+        state0["smois"][20:24, :, :] = 0.02
+        state0["sh2o"][20:24, :, :] = 0.004
+
+    st, s = _both(O, R, cfg, tables_usgs, tables_usgs_struct, 30, 0, prepare, prepare_static=prepare_static)
+    land_ice = (st["xice"] >= 0.5) & (st["xland"] < 1.5)
+    assert land_ice.sum() > 50 and (s["xlaixy"][land_ice] == np.float32(0.01)).all()
+
+
 def test_option_values_are_all_covered():
     seen = {}
     for o in OPTS:
@@ -188,6 +249,9 @@ def test_noahmp_init(O, R, tables_usgs_struct, name, ni, nj, run):
         O.set_math_mode(mode)
         R.set_math_mode(mode)
         A, sc = TI.init_case(name, ni, nj, run)[3:]
+        A["snowh"][::3, ::2], A["snow"][::3, ::2] = 0.03, 6.0       # one snow layer
+        A["snowh"][1::3, 1::2], A["snow"][1::3, 1::2] = 0.10, 25.0  # two
+        A["snowh"][2::3, ::5], A["snow"][2::3, ::5] = 0.012, 2.0    # too thin for a layer
         B = TI.clone(A)
         rc, step_o = O.init(A, sc, tables_usgs_struct)
         step_r = R.init(B, sc)
@@ -205,12 +269,17 @@ def test_wtable_coupled_with_the_column_physics(O, R, tables_usgs, tables_usgs_s
         R.set_math_mode(mode)
         cfg = _cfg(name, ni, nj, iopt_run=5)
         xp, st, sa = make_case(cfg, tables_usgs)
-        sa["smoiseq"][...] = 0.8 * sa["smois"]
-        sa["zwtxy"][...] = -3.0
-        sa["smcwtdxy"][...] = 0.3
         sb = clone_state(sa)
         wa, wsc = S.groundwater_fields(cfg, st, sa)
         wb, _ = S.groundwater_fields(cfg, st, sb)
+        # water tables from inside the top soil layer to far below the resolved soil, next to each other, so that
+        # the lateral flow moves them both ways through the layers: the branches of UPDATEWTD
+        jj, ii = np.meshgrid(np.arange(nj), np.arange(ni), indexing="ij")
+        for s_ in (sa, sb):
+            s_["zwtxy"][...] = (-0.05 - 9.0 * (((jj * 7 + ii * 3) % 23) / 22.0) ** 2).astype(np.float32)
+            s_["smcwtdxy"][...] = 0.3
+        for w_ in (wa, wb):
+            w_["fdepth"][...] = 400.0
         for step in range(1, 7):
             frc = S.forcing(xp, cfg, step, st)
             arr, sc = S.args_from(cfg, st, frc, sa, step)
