@@ -69,21 +69,26 @@ struct ref_fatal : std::runtime_error { using std::runtime_error::runtime_error;
 inline int F_ABS(int a) { return a < 0 ? -a : a; }
 inline float F_ABS(float a) { return __builtin_fabsf(a); }
 inline double F_ABS(double a) { return __builtin_fabs(a); }
-inline float F_SQRT(float a) { return __builtin_sqrtf(a); }
+inline float F_SQRT(float a);
 inline double F_SQRT(double a) { return __builtin_sqrt(a); }
-#define REF_MATH1(NAME, port, lm)                                                    \
-  inline float NAME(float x) { return ref_math_mode ? nmpm::port(x) : lm##f(x); }   \
+#ifdef NMO_OPCOUNT
+#define REF_TICK(cls) nmo_count::tick(nmo_count::cls)  // the op-counting instantiation tallies the transcendentals too
+#else
+#define REF_TICK(cls) ((void)0)
+#endif
+#define REF_MATH1(NAME, port, lm, cls)                                                                 \
+  inline float NAME(float x) { REF_TICK(cls); return ref_math_mode ? nmpm::port(x) : lm##f(x); }      \
   inline double NAME(double x) { return lm(x); }
-REF_MATH1(F_EXP, expf_, __builtin_exp)
-REF_MATH1(F_LOG, logf_, __builtin_log)
-REF_MATH1(F_LOG10, log10f_, __builtin_log10)
-REF_MATH1(F_SIN, sinf_, __builtin_sin)
-REF_MATH1(F_COS, cosf_, __builtin_cos)
-REF_MATH1(F_TAN, tanf_, __builtin_tan)
-REF_MATH1(F_ATAN, atanf_, __builtin_atan)
-REF_MATH1(F_ASIN, asinf_, __builtin_asin)
-REF_MATH1(F_ACOS, acosf_, __builtin_acos)
-REF_MATH1(F_TANH, tanhf_, __builtin_tanh)
+REF_MATH1(F_EXP, expf_, __builtin_exp, EXP)
+REF_MATH1(F_LOG, logf_, __builtin_log, LOG)
+REF_MATH1(F_LOG10, log10f_, __builtin_log10, LOG10)
+REF_MATH1(F_SIN, sinf_, __builtin_sin, SIN)
+REF_MATH1(F_COS, cosf_, __builtin_cos, COS)
+REF_MATH1(F_TAN, tanf_, __builtin_tan, TAN)
+REF_MATH1(F_ATAN, atanf_, __builtin_atan, ATAN)
+REF_MATH1(F_ASIN, asinf_, __builtin_asin, ASIN)
+REF_MATH1(F_ACOS, acosf_, __builtin_acos, ACOS)
+REF_MATH1(F_TANH, tanhf_, __builtin_tanh, TANH)
 // The reference's own gfortran configuration (arch/makefile.in.linux.*.gcc: F90FLAGS without -O) compiles without
 // optimisation, so x**y stays a libm call even for a constant y (no pow(x,2.0) -> x*x folding) and x**n is libgcc's
 // __powisf2 (square-and-multiply) whatever n is -- not the power-tree expansion -O2 would substitute for a constant
@@ -91,7 +96,7 @@ REF_MATH1(F_TANH, tanhf_, __builtin_tanh)
 // optimisation level this file is compiled with.
 float ref_powf(float x, float y);    // out of line (ref_shim.cpp): never folded
 double ref_pow(double x, double y);
-inline float F_POW(float x, float y) { return ref_math_mode ? float(nmpm::powf_(x, y)) : float(ref_powf(x, y)); }
+inline float F_POW(float x, float y) { REF_TICK(POW); return ref_math_mode ? float(nmpm::powf_(x, y)) : float(ref_powf(x, y)); }
 inline double F_POW(double x, double y) { return ref_math_mode ? nmpm::pow_d(x, y) : ref_pow(x, y); }
 template <class T>
 inline T ref_powi(T x, int m) {
@@ -128,3 +133,4 @@ inline int F_CEILING(float a) { return (int)__builtin_ceilf(a); }
 inline int F_FLOOR(float a) { return (int)__builtin_floorf(a); }
 inline bool F_ISNAN(float a) { return a != a; }
 inline bool F_ISNAN(double a) { return a != a; }
+inline float F_SQRT(float a) { REF_TICK(SQRT); return __builtin_sqrtf(a); }
