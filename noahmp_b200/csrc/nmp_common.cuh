@@ -38,7 +38,13 @@
 #define NMP_PHASE_MAJOR() __syncthreads()
 #elif NMP_PHASE_SYNC == 2
 #define NMP_PHASE() ((void)0)
+// NMP_PHASE_GROUP = g > 0 (experiment): only groups of g threads of a block keep in step (named barriers 1..), so a
+// slow warp holds back g/32 - 1 others instead of the whole block
+#if defined(NMP_PHASE_GROUP) && NMP_PHASE_GROUP > 0
+#define NMP_PHASE_MAJOR() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / NMP_PHASE_GROUP)), "n"(NMP_PHASE_GROUP) : "memory")
+#else
 #define NMP_PHASE_MAJOR() __syncthreads()
+#endif
 #else
 #define NMP_PHASE() ((void)0)
 #define NMP_PHASE_MAJOR() ((void)0)
