@@ -616,6 +616,8 @@ noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int
   if (env && (!strcmp(env, "parity") || !strcmp(env, "1"))) ctx->math_mode = 1;
   env = getenv("NOAHMP_B200_PIN");
   if (env && !strcmp(env, "0")) ctx->pin_host = false;
+  env = getenv("NOAHMP_B200_REBIN");  // steps between two re-binnings of the land columns (0 = never); tuning aid
+  if (env && atoi(env) >= 0) ctx->rebin_interval = atoi(env);
   env = getenv("NOAHMP_B200_PIN_BUDGET_GB");
   if (env && atof(env) > 0.) ctx->pin_budget = (size_t)(atof(env) * 1073741824.0);
   bool ok = true;
