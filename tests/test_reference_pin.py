@@ -294,6 +294,101 @@ def test_wtable_coupled_with_the_column_physics(O, R, tables_usgs, tables_usgs_s
         assert np.abs(wa["qslat"]).max() > 0
 
 
+# ---- leaf routines over input ranges the synthetic forcing never visits ------------------------------------------------
+
+def test_leaf_routines_over_wide_ranges(O, R, tables_usgs_struct):
+    """ESAT from -90 to +70 C, TDFCND and FRH2O (Koren99 Newton iteration) over the soil classes and every wetness,
+    ROSR12 on random diagonally dominant systems of 1..7 unknowns, COMBO on random layer pairs, STOMATA over light /
+    temperature / humidity: the reference's routine, called by name, against the oracle's probe of the same routine."""
+    import ctypes as C
+    L = O.lib()
+    rng = np.random.default_rng(7)
+    L.nmo_tdfcnd.argtypes = [C.c_float] * 4
+    L.nmo_tdfcnd.restype = C.c_float
+    L.nmo_frh2o.argtypes = [C.c_float] * 6
+    L.nmo_frh2o.restype = C.c_float
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        out4 = (C.c_float * 4)()
+        for t in np.linspace(-90.0, 70.0, 321, dtype=np.float32):
+            L.nmo_esat(C.c_float(t), out4)
+            assert [np.float32(v) for v in out4] == [np.float32(v) for v in R.call("ESAT", float(t), 0.0, 0.0, 0.0, 0.0)[1:]]
+        T = tables_usgs_struct
+        for k in range(400):
+            s = int(rng.integers(0, 12))
+            smcmax, quartz, bexp, psisat = T.maxsmc[s], T.qtz[s], T.bb[s], T.satpsi[s]
+            smc = np.float32(rng.uniform(0.02, 1.0) * smcmax)
+            sh2o = np.float32(rng.uniform(0.0, 1.0) * smc)
+            R.var("NOAHMP_GLOBALS.SMCMAX")[0] = smcmax
+            R.var("NOAHMP_GLOBALS.QUARTZ")[0] = quartz
+            R.var("NOAHMP_GLOBALS.BEXP")[0] = bexp
+            R.var("NOAHMP_GLOBALS.PSISAT")[0] = psisat
+            assert np.float32(L.nmo_tdfcnd(smc, sh2o, smcmax, quartz)) == np.float32(R.call("TDFCND", 0.0, float(smc), float(sh2o))[0])
+            tk = np.float32(rng.uniform(235.0, 274.5))
+            assert np.float32(L.nmo_frh2o(tk, smc, sh2o, bexp, psisat, smcmax)) == \
+                np.float32(R.call("FRH2O", 0.0, float(tk), float(smc), float(sh2o))[0]), (mode, k)
+        for k in range(200):
+            n = int(rng.integers(1, 8))
+            a, c_ = rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-1, 1, n).astype(np.float32)
+            b = (np.abs(a) + np.abs(c_) + rng.uniform(0.1, 2, n)).astype(np.float32)
+            d = rng.uniform(-5, 5, n).astype(np.float32)
+            x = np.zeros(n, np.float32)
+            L.nmo_rosr12(n, a.ctypes.data, b.ctypes.data, c_.ctypes.data, d.ctypes.data, x.ctypes.data)
+            top = 4 - n + 1
+            P, A, B, Cc, D, DEL = (np.zeros(7, np.float32) for _ in range(6))
+            A[top + 2:], B[top + 2:], Cc[top + 2:], D[top + 2:] = a, b, c_, d
+            R.call("ROSR12", P, A, B, Cc, D, DEL, top, 4, 3)
+            assert (P[top + 2:] == x).all(), (mode, k)
+        for k in range(200):
+            v = np.array([rng.uniform(0.01, 0.3), rng.uniform(0, 20), rng.uniform(0, 60), rng.uniform(240, 273.16)], np.float32)
+            w = np.array([rng.uniform(0.01, 0.3), rng.uniform(0, 20), rng.uniform(0, 60), rng.uniform(240, 273.16)], np.float32)
+            want = R.call("COMBO", *[float(q) for q in v], *[float(q) for q in w])[:4]
+            L.nmo_combo(v.ctypes.data, w.ctypes.data)
+            assert [np.float32(q) for q in want] == list(v), (mode, k)
+
+
+def test_stomata_and_twostream_over_wide_ranges(O, R, tables_usgs_struct):
+    """STOMATA (Ball-Berry / Farquhar, the CI iteration) over light, leaf temperature, humidity and vegetation type;
+    TWOSTREAM over sun angle, leaf area, wetness and the three canopy-gap options."""
+    import ctypes as C
+    L = O.lib()
+    rng = np.random.default_rng(11)
+    L.nmo_stomata.argtypes = [C.POINTER(_capi.NoahmpTables), C.c_int, C.c_void_p, C.c_void_p]
+    L.nmo_twostream.argtypes = [C.POINTER(_capi.NoahmpTables), C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_float] * 9 + [C.c_void_p]
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        for k in range(300):
+            veg = int(rng.choice([2, 4, 5, 7, 10, 11, 13, 14, 15, 18, 21]))
+            tv = rng.uniform(255.0, 315.0)
+            ei = 611.0 * np.exp(17.3 * (tv - 273.16) / (tv - 35.9))
+            x = np.array([rng.uniform(0.0, 400.0), rng.uniform(0.3, 1.0), tv, ei, ei * rng.uniform(0.1, 1.0),
+                          tv + rng.uniform(-5, 5), rng.uniform(60000.0, 103000.0), 0.0, 0.0, float(rng.integers(0, 2)),
+                          rng.uniform(0.0, 1.0), rng.uniform(5.0, 300.0)], np.float32)
+            x[7], x[8] = np.float32(0.209) * x[6], np.float32(395e-6) * x[6]
+            out = np.zeros(2, np.float32)
+            L.nmo_stomata(C.byref(tables_usgs_struct), veg, x.ctypes.data, out.ctypes.data)
+            r = R.call("STOMATA", veg, 1.0e-6, float(x[0]), float(x[1]), 1, 1, *[float(q) for q in x[2:]], 0.0, 0.0)
+            assert [np.float32(r[-2]), np.float32(r[-1])] == list(out), (mode, k, veg)
+        for k in range(300):
+            veg = int(rng.choice([2, 4, 5, 7, 10, 11, 13, 14, 15, 18, 21]))
+            opt_rad, ib, ic = int(rng.integers(1, 4)), int(rng.integers(1, 3)), int(rng.integers(0, 2))
+            cosz, vai, fwet = rng.uniform(0.001, 1.0), rng.uniform(0.05, 7.0), rng.uniform(0.0, 1.0)
+            tv, agd, agi = rng.uniform(250.0, 300.0), rng.uniform(0.05, 0.8), rng.uniform(0.05, 0.8)
+            rho, tau, fveg = rng.uniform(0.05, 0.5), rng.uniform(0.01, 0.4), rng.uniform(0.05, 1.0)
+            out = np.zeros(5, np.float32)
+            L.nmo_twostream(C.byref(tables_usgs_struct), opt_rad, ib, ic, veg, cosz, vai, fwet, tv, agd, agi, rho, tau, fveg,
+                            out.ctypes.data)
+            R.var("NOAHMP_GLOBALS.OPT_RAD")[0] = opt_rad
+            two = lambda v: np.full(2, v, np.float32)
+            FAB, FRE, FTD, FTI, FREV, FREG = (np.zeros(2, np.float32) for _ in range(6))
+            r = R.call("TWOSTREAM", ib, ic, veg, cosz, vai, fwet, tv, two(agd), two(agi), two(rho), two(tau), fveg, 1, 1, 1,
+                       FAB, FRE, FTD, FTI, 0.0, FREV, FREG, 0.0, 0.0)
+            got = [FAB[ib - 1], FRE[ib - 1], FTD[ib - 1], FTI[ib - 1], np.float32(r[19])]
+            assert got == list(out), (mode, k, opt_rad, ib, ic)
+
+
 # ---- the committed vectors: no reference needed ----------------------------------------------------------------------
 
 def golden():
