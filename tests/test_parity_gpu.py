@@ -120,6 +120,41 @@ def test_reference_golden_vectors(built, tables_usgs):
         m.close()
 
 
+@pytest.mark.parametrize("name,ni,nj,steps,extra", [
+    ("C3", 96, 64, 24, {}),
+    ("C4", 96, 64, 24, {"glacier_frac": 0.25, "snow_frac": 0.4, "t_base": 268.0}),
+    ("C2", 116, 112, 12, {}),
+])
+def test_cuda_equals_translated_reference(built, tables_usgs, name, ni, nj, steps, extra):
+    """The CUDA PARITY build against the reference's own Fortran text (machine-translated and compiled,
+    oracle/_ref/libnoahmp_ref.so, portable math), side by side on the same forcing, every word of every INOUT / OUT
+    array after every step -- the hand-written oracle is not in this loop."""
+    import noahmp_b200
+    from oracle.ref import refmodel
+    so = refmodel.build()
+    if so is None:
+        pytest.skip("oracle/_ref/libnoahmp_ref.so is not here and there is no reference tree to build it from")
+    R = refmodel.RefModel(so)
+    R.set_tables(_capi.tables_from_dict(tables_usgs))
+    R.set_math_mode(1)
+    cfg = _cfg(name, ni, nj)
+    for k, v in extra.items():
+        setattr(cfg, k, v)
+    xp, st, state0 = make_case(cfg, tables_usgs)
+    s_ref, s_gpu = clone_state(state0), clone_state(state0)
+    m = _model(tables_usgs, (cfg.ni, cfg.nj), noahmp_b200.MATH_PARITY)
+    for step in range(1, steps + 1):
+        frc = S.forcing(xp, cfg, step, st)
+        arr, sc = S.args_from(cfg, st, frc, s_ref, step)
+        R.noahmplsm(arr, sc)
+        arr2, sc2 = S.args_from(cfg, st, frc, s_gpu, step)
+        status = m.noahmplsm(arr2, sc2)
+        assert status.code == 0, (step, status.code, status.i, status.j)
+        rep = diff_report(s_ref, s_gpu)
+        assert not rep, f"step {step}: {rep}"
+    m.close()
+
+
 @pytest.mark.parametrize("opts", [
     dict(idveg=1, iopt_crs=2, iopt_btr=2, iopt_run=2, iopt_sfc=2, iopt_frz=2, iopt_inf=2, iopt_rad=1, iopt_alb=1,
          iopt_snf=2, iopt_tbot=1, iopt_stc=2),
