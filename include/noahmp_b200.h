@@ -229,8 +229,9 @@ int noahmp_b200_unpin(noahmp_b200_ctx* ctx, const void* host_array);
  * binned one and 1 fall back to it. */
 int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
 /* Divergence control (north_star item 4): in RESIDENT mode the land columns are physically re-ordered every
- * `interval` steps (default 20, 0 = never), inside their row chunk, into bins of equal snow-layer count and canopy
- * tile computed / not computed in the previous step, so the threads of a block take the same branches.  Results do
+ * `interval` steps (default 20, 0 = never), inside eighths of their row chunk (bands of the grid-order planes that fit
+ * the L2), into bins of equal snow-layer count and canopy tile computed / not computed in the previous step, so the
+ * threads of a block take the same branches.  Results do
  * not depend on the order; noahmp_b200_column_map returns the current one.  The environment variable
  * NOAHMP_B200_REBIN sets the initial interval (a tuning aid: profiles/r02_rebin_interval.log). */
 int noahmp_b200_set_rebin(noahmp_b200_ctx* ctx, int interval);

@@ -119,11 +119,13 @@ struct noahmp_b200_ctx {
   // column re-binning (divergence control): land columns are physically re-ordered inside each row chunk by
   // (canopy tile computed in the previous step yes/no, snow-layer count)
   int rebin_interval = 20, steps_since_rebin = 0, rebins = 0, bin_chunks = 0;
+  int bin_sub = 8;  // row groups per chunk that get bins of their own (NOAHMP_B200_BIN_SUB; see bin_key_kernel)
   bool binned = false;
   float* d_state2 = nullptr;               // PERMUTE_GROUP scratch planes of the re-binning
   std::vector<int> moved_planes;           // planes the re-binning permutes (INOUT + internal)
   cudaEvent_t ev_rebin = nullptr;
   unsigned char* d_plane_kind = nullptr;
+  std::vector<int> h_chunk;  // staging of bin_key_kernel's chunk table (kept alive for the asynchronous copy)
   int *d_cell2 = nullptr, *d_keys = nullptr, *d_keys2 = nullptr, *d_perm = nullptr, *d_iota = nullptr, *d_chunk = nullptr;
   std::vector<int> ch_land, ch_glac, ch_sea;  // compact range boundaries of the row chunks (size nchunks+1)
   std::vector<int> fetch;                  // fields refreshed on the host by every noahmplsm call
@@ -616,6 +618,8 @@ noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int
   if (env && (!strcmp(env, "parity") || !strcmp(env, "1"))) ctx->math_mode = 1;
   env = getenv("NOAHMP_B200_PIN");
   if (env && !strcmp(env, "0")) ctx->pin_host = false;
+  env = getenv("NOAHMP_B200_BIN_SUB");
+  if (env && atoi(env) >= 1 && atoi(env) <= 8) ctx->bin_sub = atoi(env);
   env = getenv("NOAHMP_B200_REBIN");  // steps between two re-binnings of the land columns (0 = never); tuning aid
   if (env && atoi(env) >= 0) ctx->rebin_interval = atoi(env);
   env = getenv("NOAHMP_B200_PIN_BUDGET_GB");
@@ -898,12 +902,21 @@ static int chunk_ranges(noahmp_b200_ctx* ctx, int nchunks, ChunkRanges* out) {
   return 0;
 }
 
+// chunk_first[0..nchunks]: first compact column of every row chunk; chunk_first[80 + c]: its first row.  With nsub > 1
+// every chunk is cut into nsub row groups that are binned separately: a bin then sweeps a band of the grid-order planes
+// (forcing, groundwater inputs) small enough to stay in L2 until the next bin of the same band reads it again.
 __global__ void bin_key_kernel(const float* __restrict__ state, long long np, int nland, const int* __restrict__ chunk_first,
-                               int nchunks, int* __restrict__ keys, int* __restrict__ iota) {
+                               int nchunks, int nsub, const int* __restrict__ cell, int ni, int* __restrict__ keys,
+                               int* __restrict__ iota) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nland) return;
   int c = 0;
   while (c + 1 < nchunks && n >= chunk_first[c + 1]) ++c;
+  if (nsub > 1) {
+    const int r0 = chunk_first[80 + c], r1 = chunk_first[80 + c + 1];
+    const int j = cell[n] / ni;
+    c = c * nsub + min(nsub - 1, (int)((long long)(j - r0) * nsub / max(r1 - r0, 1)));
+  }
   const int isnow = __float_as_int(state[(long long)NMP_SLOT(isnowxy) * np + n]);
   const int prev = __float_as_int(state[(long long)PLANE_PREV_ITERS * np + n]);
   // The number of canopy Newton passes itself is not a useful key: it is unpredictable from one step to the next
@@ -967,7 +980,7 @@ static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
     CK(cudaMalloc(&ctx->d_keys2, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_perm, sizeof(int) * ctx->ncell));
     CK(cudaMalloc(&ctx->d_iota, sizeof(int) * ctx->ncell));
-    CK(cudaMalloc(&ctx->d_chunk, sizeof(int) * 80));
+    CK(cudaMalloc(&ctx->d_chunk, sizeof(int) * 160));
     ctx->moved_planes.clear();
     std::vector<unsigned char> kind(NPLANES_ALLOC, 0);
     for (int f = 0; f < NFIELDS; ++f)
@@ -976,7 +989,7 @@ static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
       if (kind[pl] == NMP_K_INOUT && pl < PLANE_HANDOFF0) ctx->moved_planes.push_back(pl);
     size_t need = 0;
     int bits = 5;
-    while ((1 << (bits - 5)) < 64) ++bits;
+    while ((1 << (bits - 5)) < 64 * 8) ++bits;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
     if (need > ctx->cub_bytes) {
       if (ctx->d_cub) CK(cudaFree(ctx->d_cub));
@@ -984,12 +997,18 @@ static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
       ctx->cub_bytes = need;
     }
   }
-  CK(cudaMemcpyAsync(ctx->d_chunk, ctx->ch_land.data(), sizeof(int) * (nch + 1), cudaMemcpyHostToDevice, s));
+  ctx->h_chunk.assign(160, 0);
+  for (int c = 0; c <= nch && c < 80; ++c) {
+    ctx->h_chunk[c] = ctx->ch_land[c];
+    ctx->h_chunk[80 + c] = chunk_row(ctx, c, nch);
+  }
+  CK(cudaMemcpyAsync(ctx->d_chunk, ctx->h_chunk.data(), sizeof(int) * 160, cudaMemcpyHostToDevice, s));
   const int T = 256;
-  bin_key_kernel<<<(nland + T - 1) / T, T, 0, s>>>(ctx->d_state, np, nland, ctx->d_chunk, nch, ctx->d_keys, ctx->d_iota);
+  bin_key_kernel<<<(nland + T - 1) / T, T, 0, s>>>(ctx->d_state, np, nland, ctx->d_chunk, nch, ctx->bin_sub, ctx->d_cell,
+                                                   ctx->ni, ctx->d_keys, ctx->d_iota);
   ctx->launches++;
   int bits = 5;
-  while ((1 << (bits - 5)) < nch) ++bits;
+  while ((1 << (bits - 5)) < nch * ctx->bin_sub) ++bits;
   size_t need = ctx->cub_bytes;
   // stable LSD radix sort: columns of equal key keep their current relative order
   CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, need, ctx->d_keys, ctx->d_keys2, ctx->d_iota, ctx->d_perm, nland, 0, bits, s));
