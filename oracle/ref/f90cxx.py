@@ -473,7 +473,7 @@ def split_top(s, sep=","):
         elif ch == ")":
             depth -= 1
             cur += ch
-        elif ch == sep and depth == 0 and not (sep == "/" and False):
+        elif ch == sep and depth == 0:
             parts.append(cur)
             cur = ""
         else:
@@ -694,7 +694,7 @@ def _skip_chain(self):
 Scope.skip_chain = _skip_chain
 
 
-def split_decls(scope):
+def _split_decls_impl(scope):
     """separate the specification part from the executable part; fill the symbol table"""
     body = []
     for no, label, st in scope.body:
@@ -1629,8 +1629,6 @@ class Emitter:
 
     def emit_sub(self, sub, ind, as_lambda=False):
         split_decls(sub)
-        for isub in sub.subs.values():
-            pass
         if as_lambda:
             self.w(ind, "auto S_%s = [&]%s -> void {" % (sub.name, self.signature(sub)))
         else:
@@ -1674,7 +1672,7 @@ class Emitter:
         subs = [s for s in mod.subs.values() if not s.skip]
         # prototypes need the dummies' types: parse the specification parts first
         for s in subs:
-            split_decls_once(s)
+            split_decls(s)
         for s in subs:
             self.w(0, "void S_%s%s;" % (s.name, self.signature(s)))
         self.w(0, "}  // namespace M_%s" % mod.name)
@@ -1689,21 +1687,15 @@ class Emitter:
         self.w(0, "")
 
 
-def split_decls_once(scope):
+def split_decls(scope):
+    """specification part -> symbol table, once per scope (and its contained procedures)"""
     if getattr(scope, "_split", False):
         return
     scope._split = True
-    _orig_split_decls(scope)
+    _split_decls_impl(scope)
     for isub in scope.subs.values():
         if not isub.skip:
-            split_decls_once(isub)
-
-
-_orig_split_decls = split_decls
-
-
-def split_decls(scope):  # noqa: F811  (idempotent wrapper)
-    split_decls_once(scope)
+            split_decls(isub)
 
 
 def top_name(sc):
