@@ -178,7 +178,16 @@ def test_long_melt_season(O, R, tables_usgs, tables_usgs_struct):
     PHASECHANGE's sign reversals), on vegetated and glacier columns."""
     cfg = _cfg("C3", 48, 32, iopt_snf=3)
     cfg.t_base, cfg.start, cfg.lat, cfg.snow_frac, cfg.glacier_frac = 278.0, (2017, 4, 20, 0), (38.0, 50.0), 0.9, 0.15
-    st, s = _both(O, R, cfg, tables_usgs, tables_usgs_struct, 192, 0)
+    def prepare(state0):   # a nearly empty top layer on some three-layer packs: COMBINE merges it downwards
+        top = (state0["isnowxy"] == -3)
+        top[:, ::2] = False
+        removed = state0["snicexy"][:, 0, :][top] + state0["snliqxy"][:, 0, :][top] - np.float32(0.05)
+        state0["snow"][top] = state0["snow"][top] - removed      # SNEQV stays the sum of the layers
+        state0["sneqvoxy"][top] = state0["snow"][top]
+        state0["snicexy"][:, 0, :][top] = 0.05
+        state0["snliqxy"][:, 0, :][top] = 0.0
+
+    st, s = _both(O, R, cfg, tables_usgs, tables_usgs_struct, 192, 0, prepare)
     assert (s["isnowxy"] == 0).mean() > 0.15 and set(np.unique(s["isnowxy"])) >= {-3, -2, -1, 0}
 
 
@@ -187,7 +196,12 @@ def test_glacier_in_summer(O, R, tables_usgs, tables_usgs_struct):
     PHASECHANGE_GLACIER.  Leap year (YEARLEN = 366)."""
     cfg = _cfg("C4", 40, 30)
     cfg.t_base, cfg.start, cfg.lat, cfg.snow_frac, cfg.glacier_frac, cfg.water_frac = 276.5, (2016, 7, 5, 0), (60.0, 72.0), 0.3, 0.6, 0.1
-    _both(O, R, cfg, tables_usgs, tables_usgs_struct, 96, 1)
+    def prepare(state0):   # thawed ice layers above and below frozen ones: the four redistribution sweeps
+        state0["tslb"][::2, 0, :] = 274.2
+        state0["tslb"][::2, 2, :] = 273.6
+        state0["tslb"][1::2, 1, :] = 273.9
+
+    _both(O, R, cfg, tables_usgs, tables_usgs_struct, 96, 1, prepare)
 
 
 def test_sea_ice_points_soil_type_14_and_dry_soil(O, R, tables_usgs, tables_usgs_struct):
@@ -252,6 +266,8 @@ def test_noahmp_init(O, R, tables_usgs_struct, name, ni, nj, run):
         A["snowh"][::3, ::2], A["snow"][::3, ::2] = 0.03, 6.0       # one snow layer
         A["snowh"][1::3, 1::2], A["snow"][1::3, 1::2] = 0.10, 25.0  # two
         A["snowh"][2::3, ::5], A["snow"][2::3, ::5] = 0.012, 2.0    # too thin for a layer
+        A["snowh"][2::3, 1::5], A["snow"][2::3, 1::5] = 0.60, 150.0 # three
+        A["snowh"][2::3, 3::5], A["snow"][2::3, 3::5] = 0.35, 80.0  # three, the thinner split
         B = TI.clone(A)
         rc, step_o = O.init(A, sc, tables_usgs_struct)
         step_r = R.init(B, sc)
@@ -292,6 +308,42 @@ def test_wtable_coupled_with_the_column_physics(O, R, tables_usgs, tables_usgs_s
             bad += ["state." + n for n in sa if not _same(sa[n], sb[n])]
             assert not bad, (mode, step, bad)
         assert np.abs(wa["qslat"]).max() > 0
+
+
+def test_wtable_rising_and_falling_through_the_layers(O, R, tables_usgs, tables_usgs_struct):
+    """WTABLE_mmf_noahmp alone on flat terrain without rivers, water tables in a checkerboard of neighbouring depths at
+    every level of the column (inside each soil layer, just below the soil, deep): half of the columns gain water and
+    fill their layers upwards, the others drain — UPDATEWTD's rising branches, which the coupled runs reach rarely."""
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        cfg = _cfg("C2", 48, 40, iopt_run=5)
+        cfg.water_frac = 0.0
+        xp, st, sa = make_case(cfg, tables_usgs)
+        sb = clone_state(sa)
+        wa, wsc = S.groundwater_fields(cfg, st, sa)
+        wb, _ = S.groundwater_fields(cfg, st, sb)
+        jj, ii = np.meshgrid(np.arange(cfg.nj), np.arange(cfg.ni), indexing="ij")
+        level = np.array([-0.05, -0.25, -0.7, -1.5, -2.2, -3.5, -8.0], np.float32)[(jj // 6) % 7]
+        wtd = (level - np.float32(0.6) * ((ii + jj) % 2) * np.minimum(np.float32(1.0), -level)).astype(np.float32)
+        for s_, w_ in ((sa, wa), (sb, wb)):
+            s_["zwtxy"][...] = wtd
+            s_["smcwtdxy"][...] = 0.25
+            s_["smois"][...] = (0.5 * s_["smoiseq"] / 0.8 + 0.05).astype(np.float32)   # room to fill
+            # ... except in the eastern half, a hair below saturation: what arrives spills into the layer above
+            smcmax = np.asarray(tables_usgs_struct.maxsmc, np.float32)[st["isltyp"] - 1]
+            s_["smois"][:, :, cfg.ni // 2:] = (smcmax - np.float32(2e-4))[:, None, cfg.ni // 2:]
+            s_["smcwtdxy"][:, cfg.ni // 2:] = (smcmax - np.float32(2e-4))[:, cfg.ni // 2:]
+            s_["sh2o"][...] = s_["smois"]
+            w_["topo"][...] = 100.0
+            w_["fdepth"][...] = 300.0
+            w_["rivercond"][...] = 0.0
+        for step in range(1, 13):
+            O.wtable(wa, wsc, tables_usgs_struct)
+            R.wtable(wb, wsc)
+            bad = [n for n in wa if isinstance(wa[n], np.ndarray) and not _same(wa[n], wb[n])]
+            assert not bad, (mode, step, bad)
+        assert (sa["zwtxy"] > wtd).sum() > 100 and (sa["zwtxy"] < wtd).sum() > 100
 
 
 # ---- leaf routines over input ranges the synthetic forcing never visits ------------------------------------------------

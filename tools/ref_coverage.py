@@ -48,6 +48,7 @@ def main():
         P.test_noahmp_init(O, R, ts, *a)
     for a in [("C4", 40, 30), ("C3", 96, 64), ("C2", 80, 60)]:
         P.test_wtable_coupled_with_the_column_physics(O, R, td, ts, *a)
+    P.test_wtable_rising_and_falling_through_the_layers(O, R, td, ts)
     ran.append("all cases of tests/test_reference_pin.py held (oracle == translated reference)")
 
     R.lib.ref_cover_map.restype = C.POINTER(C.c_ubyte)
