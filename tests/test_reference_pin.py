@@ -154,7 +154,7 @@ def test_every_accepted_option_value(O, R, tables_usgs, tables_usgs_struct, k):
 
 # other climates than the configurations' own: (name, base, t_base, start, latitudes, snow_frac, glacier_frac, options)
 CLIMATES = [
-    ("tropical_july", "C2", 301.0, (2017, 7, 15, 0), (-10.0, 15.0), 0.0, 0.0, {}),
+    ("tropical_july", "C2", 301.0, (2017, 7, 15, 0), (-10.0, 15.0), 0.0, 0.0, dict(iopt_snf=2)),
     ("polar_winter", "C3", 243.0, (2017, 1, 10, 0), (60.0, 80.0), 0.9, 0.3, {}),
     ("spring_melt", "C3", 272.5, (2017, 4, 10, 6), (40.0, 55.0), 0.8, 0.1, dict(iopt_alb=1, iopt_snf=3)),
     ("summer_noon_dynveg", "C3", 295.0, (2017, 7, 1, 12), (30.0, 45.0), 0.0, 0.0, dict(iopt_rad=1, iopt_btr=2)),
@@ -186,6 +186,20 @@ def test_long_melt_season(O, R, tables_usgs, tables_usgs_struct):
         state0["sneqvoxy"][top] = state0["snow"][top]
         state0["snicexy"][:, 0, :][top] = 0.05
         state0["snliqxy"][:, 0, :][top] = 0.0
+        one = (state0["isnowxy"] == -1)                          # a single, nearly empty layer: the pack vanishes
+        one[:, 1::2] = False
+        removed = state0["snicexy"][:, 2, :][one] + state0["snliqxy"][:, 2, :][one] - np.float32(0.05)
+        state0["snow"][one] = state0["snow"][one] - removed
+        state0["sneqvoxy"][one] = state0["snow"][one]
+        state0["snicexy"][:, 2, :][one] = 0.05
+        state0["snliqxy"][:, 2, :][one] = 0.0
+        deep = (state0["isnowxy"] == -3)                         # more than 2000 mm of snow: the excess flows off
+        deep[:, 1::3] = False
+        deep[:, 2::3] = False
+        deep &= ~top
+        state0["snicexy"][:, 2, :][deep] += 2100.0
+        state0["snow"][deep] += 2100.0
+        state0["sneqvoxy"][deep] = state0["snow"][deep]
 
     st, s = _both(O, R, cfg, tables_usgs, tables_usgs_struct, 192, 0, prepare)
     assert (s["isnowxy"] == 0).mean() > 0.15 and set(np.unique(s["isnowxy"])) >= {-3, -2, -1, 0}
