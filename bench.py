@@ -560,9 +560,13 @@ def main():
                          "peak_source": peak_src, "kernel": f"land_kernel<{model.variant}>",
                          "algorithmic_bytes_per_column_step": alg_bytes,
                          "columns_per_launch": ncol, "kernel_ms": mean_ms,
-                         "note": "step = land_kernel (+ re-binning passes every 20 steps; + glacier/sea-ice kernels when "
+                         "note": "step = land_kernel (+ the re-binning check every 20 steps and its permutation when due; + glacier/sea-ice kernels when "
                                  "present); the physics is FP32/SFU-issue and latency bound, see compute_roofline and DESIGN.md"},
             "clocks": clocks, "gpu_launches": launches_all, "census": census, "math": args.math,
+            "rebinning": {"permutations_rank0": int(model.rebins),
+                          "policy": "every 20 steps the bin keys are recomputed and the columns permuted only if more than "
+                                    "0.1 % of them left their bin (NOAHMP_B200_REBIN_MIN_CHANGED; 0 = always: +0.16 ms per "
+                                    "step on this workload, profiles/r02_notes.md)"},
         }
         if args.full_day:
             day = step_ms_max[args.steps:args.steps + RING_HOURS]

@@ -233,7 +233,10 @@ int noahmp_b200_set_chunks(noahmp_b200_ctx* ctx, int nchunks);
  * the L2), into bins of equal snow-layer count and canopy tile computed / not computed in the previous step, so the
  * threads of a block take the same branches.  Results do
  * not depend on the order; noahmp_b200_column_map returns the current one.  The environment variable
- * NOAHMP_B200_REBIN sets the initial interval (a tuning aid: profiles/r02_rebin_interval.log). */
+ * NOAHMP_B200_REBIN sets the initial interval (a tuning aid: profiles/r02_rebin_interval.log).  When a re-binning is
+ * due the library first counts how many columns left their bin (asynchronously: the answer is used by a later step)
+ * and permutes only above NOAHMP_B200_REBIN_MIN_CHANGED (default 0.001 of the land columns; 0 = always).
+ * noahmp_b200_rebin_count counts the permutations done. */
 int noahmp_b200_set_rebin(noahmp_b200_ctx* ctx, int interval);
 int noahmp_b200_rebin_count(const noahmp_b200_ctx* ctx);
 /* Refresh ONE caller array (named like the noahmp_lsm_args member, e.g. "tsk") from HBM in RESIDENT mode. */

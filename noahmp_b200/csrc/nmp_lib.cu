@@ -119,6 +119,15 @@ struct noahmp_b200_ctx {
   // column re-binning (divergence control): land columns are physically re-ordered inside each row chunk by
   // (canopy tile computed in the previous step yes/no, snow-layer count)
   int rebin_interval = 20, steps_since_rebin = 0, rebins = 0, bin_chunks = 0;
+  // A due re-binning first asks whether the order still holds: the bin keys are recomputed, the places where they
+  // decrease along the compact order counted (two per column whose bin changed), the count read back without waiting
+  // (pinned word + event, looked at in a later step) -- and the 4.9 ms permutation is done only if more than
+  // rebin_min_changed of the land columns are out of place (NOAHMP_B200_REBIN_MIN_CHANGED; 0 = always permute).
+  float rebin_min_changed = 1e-3f;
+  bool check_pending = false;
+  cudaEvent_t ev_check = nullptr;
+  int *d_viol = nullptr, *h_viol = nullptr;
+  int rebin_checks = 0, rebin_skips = 0;
   int bin_sub = 8;  // row groups per chunk that get bins of their own (NOAHMP_B200_BIN_SUB; see bin_key_kernel)
   bool binned = false;
   float* d_state2 = nullptr;               // PERMUTE_GROUP scratch planes of the re-binning
@@ -511,6 +520,7 @@ static int classify(noahmp_b200_ctx* ctx) {
   if (ctx->np) CK(cudaMemcpy(ctx->h_cell.data(), ctx->d_cell, sizeof(int) * ctx->np, cudaMemcpyDeviceToHost));
   ctx->classified = true;
   ctx->binned = false;
+  ctx->check_pending = false;
   ctx->bin_chunks = 0;
   ctx->steps_since_rebin = 0;
   return 0;
@@ -618,6 +628,8 @@ noahmp_b200_ctx* noahmp_b200_create(int device, const noahmp_tables* tables, int
   if (env && (!strcmp(env, "parity") || !strcmp(env, "1"))) ctx->math_mode = 1;
   env = getenv("NOAHMP_B200_PIN");
   if (env && !strcmp(env, "0")) ctx->pin_host = false;
+  env = getenv("NOAHMP_B200_REBIN_MIN_CHANGED");
+  if (env && atof(env) >= 0.) ctx->rebin_min_changed = (float)atof(env);
   env = getenv("NOAHMP_B200_BIN_SUB");
   if (env && atoi(env) >= 1 && atoi(env) <= 8) ctx->bin_sub = atoi(env);
   env = getenv("NOAHMP_B200_REBIN");  // steps between two re-binnings of the land columns (0 = never); tuning aid
@@ -672,6 +684,7 @@ void noahmp_b200_destroy(noahmp_b200_ctx* ctx) {
   if (ctx->comm.comm && nccl_api()) nccl_api()->CommDestroy(ctx->comm.comm);
   cudaFree(ctx->d_state2); cudaFree(ctx->d_cell2); cudaFree(ctx->d_keys); cudaFree(ctx->d_keys2);
   cudaFree(ctx->d_perm); cudaFree(ctx->d_iota); cudaFree(ctx->d_chunk); cudaFree(ctx->d_plane_kind);
+  cudaFree(ctx->d_viol); if (ctx->h_viol) cudaFreeHost(ctx->h_viol); if (ctx->ev_check) cudaEventDestroy(ctx->ev_check);
   for (auto& b : ctx->d_fb) for (auto p : b) cudaFree(p);
   cudaFree(ctx->d_lat); cudaFree(ctx->d_lon);
   for (auto e : ctx->ev_fb) if (e) cudaEventDestroy(e);
@@ -925,6 +938,13 @@ __global__ void bin_key_kernel(const float* __restrict__ state, long long np, in
   keys[n] = c * 32 + pb * 4 + min(max(-isnow, 0), 3);
   iota[n] = n;
 }
+// number of places where the bin key decreases along the compact order (0 = the columns are still sorted)
+__global__ void key_order_kernel(const int* __restrict__ keys, int nland, int* __restrict__ viol) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (n > 0 && n < nland && keys[n] < keys[n - 1]) ? 1 : 0;
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(viol, v);
+}
 // scratch[g][i] = state[planes[g]][perm[i]] for the land columns i < nland of one group of planes.  One thread moves
 // its column in PERMUTE_GROUP planes: the permutation index is read once per group and the group's gathers are in
 // flight together.  The permuted group is then copied back over the planes it came from (a dense device-to-device
@@ -997,16 +1017,53 @@ static int rebin(noahmp_b200_ctx* ctx, cudaStream_t s) {
       ctx->cub_bytes = need;
     }
   }
-  ctx->h_chunk.assign(160, 0);
-  for (int c = 0; c <= nch && c < 80; ++c) {
-    ctx->h_chunk[c] = ctx->ch_land[c];
-    ctx->h_chunk[80 + c] = chunk_row(ctx, c, nch);
-  }
-  CK(cudaMemcpyAsync(ctx->d_chunk, ctx->h_chunk.data(), sizeof(int) * 160, cudaMemcpyHostToDevice, s));
   const int T = 256;
-  bin_key_kernel<<<(nland + T - 1) / T, T, 0, s>>>(ctx->d_state, np, nland, ctx->d_chunk, nch, ctx->bin_sub, ctx->d_cell,
-                                                   ctx->ni, ctx->d_keys, ctx->d_iota);
-  ctx->launches++;
+  auto compute_keys = [&]() -> int {
+    ctx->h_chunk.assign(160, 0);
+    for (int c = 0; c <= nch && c < 80; ++c) {
+      ctx->h_chunk[c] = ctx->ch_land[c];
+      ctx->h_chunk[80 + c] = chunk_row(ctx, c, nch);
+    }
+    CK(cudaMemcpyAsync(ctx->d_chunk, ctx->h_chunk.data(), sizeof(int) * 160, cudaMemcpyHostToDevice, s));
+    bin_key_kernel<<<(nland + T - 1) / T, T, 0, s>>>(ctx->d_state, np, nland, ctx->d_chunk, nch, ctx->bin_sub,
+                                                     ctx->d_cell, ctx->ni, ctx->d_keys, ctx->d_iota);
+    ctx->launches++;
+    return 0;
+  };
+  if (ctx->binned && ctx->rebin_min_changed > 0.f) {
+    if (!ctx->check_pending) {
+      if (!ctx->ev_check) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_check, cudaEventDisableTiming));
+        CK(cudaMalloc(&ctx->d_viol, sizeof(int)));
+        CK(cudaMallocHost((void**)&ctx->h_viol, sizeof(int)));
+      }
+      int rc = compute_keys();
+      if (rc) return rc;
+      CK(cudaMemsetAsync(ctx->d_viol, 0, sizeof(int), s));
+      key_order_kernel<<<(nland + T - 1) / T, T, 0, s>>>(ctx->d_keys, nland, ctx->d_viol);
+      ctx->launches++;
+      CK(cudaMemcpyAsync(ctx->h_viol, ctx->d_viol, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaEventRecord(ctx->ev_check, s));
+      ctx->check_pending = true;
+      ctx->rebin_checks++;
+      return 0;  // the answer is looked at when a later step comes by (no waiting here)
+    }
+    const cudaError_t q = cudaEventQuery(ctx->ev_check);
+    if (q == cudaErrorNotReady) return 0;
+    CK(q);
+    ctx->check_pending = false;
+    if ((double)*ctx->h_viol <= 2.0 * (double)ctx->rebin_min_changed * (double)nland) {
+      ctx->steps_since_rebin = 0;
+      ctx->rebin_skips++;
+      if (ctx->trace) fprintf(stderr, "[noahmp_b200 trace] re-binning skipped: %d order breaks in %d land columns\n",
+                              *ctx->h_viol, nland);
+      return 0;
+    }
+  }
+  {
+    int rc = compute_keys();
+    if (rc) return rc;
+  }
   int bits = 5;
   while ((1 << (bits - 5)) < nch * ctx->bin_sub) ++bits;
   size_t need = ctx->cub_bytes;

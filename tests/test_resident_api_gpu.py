@@ -94,10 +94,42 @@ def test_push_list_follows_host_lai(built, tables_usgs):
         m.close()
 
 
-def test_chunking_may_change_after_rebinning(built, tables_usgs):
+def test_rebinning_is_skipped_while_the_order_holds(built, tables_usgs, monkeypatch):
+    """A due re-binning first counts the places where the bin keys decrease along the compact order and permutes only
+    if more than a threshold of the columns left their bin: on a snow-free tile nothing ever does, so after the first
+    binning no further permutation happens -- and with the threshold at 0 one happens at every interval.  Either way
+    the results equal the FULL-mode results bit for bit."""
+    import noahmp_b200
+    cfg = _cfg("C2", 96, 80)
+    _, st, state0 = make_case(cfg, tables_usgs)
+    xp = S.backend()
+    counts = {}
+    ref = None
+    for thr in ("default", "0"):
+        if thr == "0":
+            monkeypatch.setenv("NOAHMP_B200_REBIN_MIN_CHANGED", "0")
+        s = clone_state(state0)
+        m = _model(tables_usgs, cfg, noahmp_b200.SYNC_RESIDENT)
+        m.set_rebin(3)
+        m.set_fetch(["tsk", "hfx"])
+        for step in range(1, 17):
+            arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, step, st), s, step)
+            assert m.noahmplsm(arr, sc).code == 0
+        counts[thr] = m.rebins
+        m.sync_host(arr, sc)
+        if ref is None:
+            ref = s
+        else:
+            assert not diff_report(ref, s)
+        m.close()
+    assert counts["default"] == 1 and counts["0"] >= 4, counts
+
+
+def test_chunking_may_change_after_rebinning(built, tables_usgs, monkeypatch):
     """After the first re-binning the columns stay inside the row chunk they were binned in; calls that ask for another
     chunk count (a different entry point, set_chunks) keep working and give the same bits."""
     import noahmp_b200
+    monkeypatch.setenv("NOAHMP_B200_REBIN_MIN_CHANGED", "0")   # permute at every interval, whether the order broke or not
     cfg = _cfg("C4", 150, 121)
     _, st, state0 = make_case(cfg, tables_usgs)
     a, b = clone_state(state0), clone_state(state0)
