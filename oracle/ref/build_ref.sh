@@ -9,7 +9,23 @@ R=${NOAHMP_REFERENCE:-/root/reference}
 mkdir -p _ref
 T=$(mktemp -d)
 trap 'rm -rf "$T"' EXIT
-python ref/f90cxx.py "$T/ref_gen.cpp" $R/util/module_model_constants.F \
+# CALC_DECLIN (driver/module_hrldas_noahmp_driver.F90) is an external procedure whose only non-arithmetic part is reading
+# day and time out of a date string: it is extracted as it stands, the string handling (the NOWDATE dummy, GETH_IDTS and
+# the three internal READs) replaced by integer dummies IDAY, IHOUR, IMINUTE, ISECOND, and wrapped into a module
+python - "$R/driver/module_hrldas_noahmp_driver.F90" "$T/ref_calc_declin.F90" <<'PY'
+import re, sys
+src = open(sys.argv[1], errors="replace").read()
+m = re.search(r"^subroutine CALC_DECLIN\(.*?^end subroutine CALC_DECLIN", src, flags=re.S | re.M | re.I)
+body = m.group(0)
+body = re.sub(r"subroutine CALC_DECLIN\(NOWDATE,", "subroutine CALC_DECLIN(IDAY, IHOUR, IMINUTE, ISECOND,", body, count=1, flags=re.I)
+keep = []
+for line in body.split("\n"):
+    if re.search(r"use MODULE_DATE_UTILITIES|NOWDATE", line, flags=re.I):
+        continue
+    keep.append(line)
+open(sys.argv[2], "w").write("MODULE REF_DRIVER_EXTRACT\nCONTAINS\n" + "\n".join(keep) + "\nEND MODULE REF_DRIVER_EXTRACT\n")
+PY
+python ref/f90cxx.py "$T/ref_gen.cpp" "$T/ref_calc_declin.F90" $R/util/module_model_constants.F \
   $R/phys/module_sf_noahmplsm.F90:skip=READ_MP_VEG_PARAMETERS,SFCDIF3,SFCDIF4 \
   $R/phys/module_sf_noahmp_glacier.F90 \
   $R/phys/module_sf_noahmp_groundwater.F90 \

@@ -455,6 +455,28 @@ def test_stomata_and_twostream_over_wide_ranges(O, R, tables_usgs_struct):
             assert got == list(out), (mode, k, opt_rad, ib, ic)
 
 
+def test_calc_declin_of_the_forcing_pipeline(O, R, tables_usgs):
+    """Row f2: CALC_DECLIN of the HRLDAS driver (module_hrldas_noahmp_driver.F90:813-863), extracted as it stands with the
+    date-string handling replaced by integer arguments (oracle/ref/build_ref.sh) and translated, against the COSZEN /
+    JULIAN of the oracle's forcing preparation: every hour of four days of the year, a latitude-longitude net."""
+    import test_forcing as TF
+    cfg = _cfg("C1", 10, 10)
+    _, st, _ = make_case(cfg, tables_usgs)
+    A, B = TF._files(cfg, st, (1, 4))
+    lat = np.linspace(-75.0, 80.0, 100, dtype=np.float32).reshape(10, 10)
+    lon = np.linspace(-179.0, 179.5, 100, dtype=np.float32).reshape(10, 10).T.copy()
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        for iday in (0, 79, 80, 171, 300, 364):
+            for hour, minute, second in ((0, 0, 0), (5, 30, 0), (12, 0, 0), (17, 45, 30), (23, 59, 59)):
+                out, julian = O.forcing(A, B, lat, lon, 1.0, iday, hour, minute, second, cfg.dt)
+                for (j, i) in ((0, 0), (3, 7), (9, 9), (5, 2), (8, 1)):
+                    r = R.call("CALC_DECLIN", iday, hour, minute, second, float(lat[j, i]), float(lon[j, i]), 0.0, 0.0)
+                    assert np.float32(r[6]) == out[0][j, i], (mode, iday, hour, j, i)
+                    assert np.float32(r[7]) == np.float32(julian)
+
+
 # ---- the committed vectors: no reference needed ----------------------------------------------------------------------
 
 def golden():
