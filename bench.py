@@ -596,7 +596,10 @@ def main():
                 "fp32": {"achieved_thread_instr_per_s": fp32_pc * colrate, "peak": fpk, "frac": f_fp32},
                 "issue": {"achieved_thread_instr_per_s": (fp32_pc + mufu_pc) * colrate, "peak": fpk, "frac": f_issue},
                 "source": "ALGORITHMIC operations per column-step counted by the op-counting instantiation of the oracle "
-                          "on the timed hours (tools/opcount.py -> profiles/r02_opcount.json: " + o.get("sample", "") + "); "
+                          "on the timed hours (tools/opcount.py -> profiles/r02_opcount.json: " + o.get("sample", "") + "; the "
+                          "reference's own text, translated and compiled with the same counting type, gives the same "
+                          "transcendental counts and adds / multiplies / divides within 0.7 %: "
+                          "profiles/r02_opcount_reference_check.txt); "
                           "fp32_instr assumes every add fuses with a multiply (lower bound), divisions and transcendentals "
                           "expanded as the production build issues them; peaks = measured FFMA and MUFU.EX2 issue rates of "
                           "this GPU type (tools/peaks.cu, profiles/r01_peaks.json); frac = the larger of the MUFU-pipe and "
