@@ -455,6 +455,81 @@ def test_stomata_and_twostream_over_wide_ranges(O, R, tables_usgs_struct):
             assert got == list(out), (mode, k, opt_rad, ib, ic)
 
 
+def test_snow_routines_on_random_packs(O, R):
+    """SNOWWATER (SNOWFALL, COMPACT, COMBINE, DIVIDE, SNOWH2O) and the glacier PHASECHANGE on random snow packs of 0-3
+    layers with thin, nearly empty, very thick and melting layers -- the layer bookkeeping branches that a model run
+    visits only now and then -- called by name in the translated reference and through the oracle's probes."""
+    import ctypes as C
+    L = O.lib()
+    rng = np.random.default_rng(23)
+    f = np.float32
+    zsoil = np.array([-0.1, -0.4, -1.0, -2.0], f)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for mode in (0, 1):
+        O.set_math_mode(mode)
+        R.set_math_mode(mode)
+        for k in range(600):
+            isnow = -int(rng.integers(0, 4))
+            dz = np.zeros(7, f)
+            snice, snliq = np.zeros(3, f), np.zeros(3, f)
+            for j in range(3 + isnow, 3):
+                dz[j] = f(rng.choice([0.012, 0.03, 0.06, 0.2, 0.6]) * rng.uniform(0.7, 1.3))
+                snice[j] = f(dz[j] * rng.uniform(50.0, 450.0)) if rng.random() > 0.25 else f(rng.uniform(0.0, 0.12))
+                snliq[j] = f(rng.uniform(0.0, 0.1) * snice[j]) if rng.random() > 0.3 else f(0.0)
+            dz[3:] = [0.1, 0.3, 0.6, 1.0]
+            zsnso = (-np.cumsum(dz[3 + isnow:])).astype(f)
+            z7 = np.zeros(7, f)
+            z7[3 + isnow:] = zsnso
+            if isnow < 0:
+                sneqv, snowh = f((snice + snliq).sum()), f(dz[:3].sum())
+            else:
+                sneqv = f(rng.choice([0.0, 0.5, 8.0, 40.0]))
+                snowh = f(sneqv / 120.0)
+            stc = rng.uniform(255.0, 273.16, 7).astype(f)
+            sh2o, sice = rng.uniform(0.05, 0.3, 4).astype(f), rng.uniform(0.0, 0.1, 4).astype(f)
+            imelt = rng.integers(0, 3, 7).astype(np.int32)
+            ficeold = rng.uniform(0.3, 1.0, 3).astype(f)
+            sc = np.array([3600.0, rng.uniform(255, 278), 0.0, 0.0, rng.uniform(0, 2e-5), rng.uniform(0, 2e-5),
+                           rng.choice([0.0, 1e-4, 1e-3])], f)
+            if rng.random() < 0.5:      # snowing
+                sc[3] = f(rng.uniform(1e-5, 2e-3))
+                sc[2] = f(sc[3] / rng.uniform(50.0, 150.0))
+            a = [x.copy() for x in (snice, snliq, sh2o, sice, stc, z7, dz)]
+            b = [x.copy() for x in (snice, snliq, sh2o, sice, stc, z7, dz)]
+            io2, out4, isn = np.array([snowh, sneqv], f), np.zeros(4, f), C.c_int(isnow)
+            L.nmo_snowwater(vp(imelt), vp(sc), vp(zsoil), vp(ficeold), C.byref(isn), vp(io2), *[vp(x) for x in a], vp(out4))
+            r = R.call("SNOWWATER", 3, 4, imelt.copy(), float(sc[0]), zsoil.copy(), float(sc[1]), float(sc[2]), float(sc[3]),
+                       float(sc[4]), float(sc[5]), float(sc[6]), ficeold.copy(), 1, 1, isnow, float(snowh), float(sneqv),
+                       *b, 0.0, 0.0, 0.0, 0.0)
+            assert r[14] == isn.value, (mode, k, isnow, r[14], isn.value)
+            assert [f(r[15]), f(r[16])] == list(io2) and [f(x) for x in r[24:28]] == list(out4), (mode, k, isnow)
+            for x, y in zip(a, b):
+                assert _same(x, y), (mode, k, isnow)
+        for k in range(400):    # land ice: layers straddling the freezing point
+            isnow = -int(rng.integers(0, 4))
+            dz = np.array([0.05, 0.1, 0.3, 0.1, 0.3, 0.6, 1.0], f)
+            fact = (3600.0 / (rng.uniform(1.0e6, 2.2e6, 7) * dz)).astype(f)
+            stc = (273.16 + rng.choice([-3.0, -0.4, 0.0, 0.3, 1.5], 7) + rng.uniform(-0.05, 0.05, 7)).astype(f)
+            snice, snliq = np.zeros(3, f), np.zeros(3, f)
+            for j in range(3 + isnow, 3):
+                snice[j], snliq[j] = f(rng.uniform(0.0, 60.0)), f(rng.uniform(0.0, 4.0))
+            sneqv = f((snice + snliq).sum()) if isnow < 0 else f(rng.choice([0.0, 3.0]))
+            snowh = f(dz[3 + isnow:3].sum()) if isnow < 0 else f(sneqv / 100.0)
+            smc, sh2o = np.ones(4, f), rng.choice([0.0, 0.02, 0.4, 1.0], 4).astype(f)   # 1.0: a layer of melt water
+            a = [x.copy() for x in (stc, snice, snliq)]
+            b = [x.copy() for x in (stc, snice, snliq)]
+            sa, sb = [smc.copy(), sh2o.copy()], [smc.copy(), sh2o.copy()]
+            se, sh, qm, po = (C.c_float(sneqv), C.c_float(snowh), C.c_float(0.0), C.c_float(0.0))
+            im_a, im_b = np.zeros(7, np.int32), np.zeros(7, np.int32)
+            L.nmo_phasechange_glacier(isnow, C.c_float(3600.0), vp(fact), vp(dz), vp(a[0]), vp(a[1]), vp(a[2]), C.byref(se),
+                                      C.byref(sh), vp(sa[0]), vp(sa[1]), C.byref(qm), vp(im_a), C.byref(po))
+            r = R.call("PHASECHANGE_GLACIER", 3, 4, isnow, 3600.0, fact.copy(), dz.copy(), b[0], b[1], b[2], float(sneqv),
+                       float(snowh), sb[0], sb[1], 0.0, im_b, 0.0)
+            assert [f(r[9]), f(r[10]), f(r[13]), f(r[15])] == [f(se.value), f(sh.value), f(qm.value), f(po.value)], (mode, k)
+            for x, y in zip(a + sa + [im_a], b + sb + [im_b]):
+                assert _same(x, y), (mode, k, isnow)
+
+
 def test_calc_declin_of_the_forcing_pipeline(O, R, tables_usgs):
     """Row f2: CALC_DECLIN of the HRLDAS driver (module_hrldas_noahmp_driver.F90:813-863), extracted as it stands with the
     date-string handling replaced by integer arguments (oracle/ref/build_ref.sh) and translated, against the COSZEN /

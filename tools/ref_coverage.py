@@ -49,6 +49,10 @@ def main():
     for a in [("C4", 40, 30), ("C3", 96, 64), ("C2", 80, 60)]:
         P.test_wtable_coupled_with_the_column_physics(O, R, td, ts, *a)
     P.test_wtable_rising_and_falling_through_the_layers(O, R, td, ts)
+    P.test_leaf_routines_over_wide_ranges(O, R, ts)
+    P.test_stomata_and_twostream_over_wide_ranges(O, R, ts)
+    P.test_snow_routines_on_random_packs(O, R)
+    P.test_calc_declin_of_the_forcing_pipeline(O, R, td)
     ran.append("all cases of tests/test_reference_pin.py held (oracle == translated reference)")
 
     R.lib.ref_cover_map.restype = C.POINTER(C.c_ubyte)
