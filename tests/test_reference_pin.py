@@ -261,6 +261,19 @@ def test_rejected_inputs_stop_both(O, R, tables_usgs, tables_usgs_struct):
     arr2, sc2 = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), clone_state(state), 1)
     with pytest.raises(RuntimeError, match="too many input soil types"):
         R.noahmplsm(arr2, sc2)
+    # a snow pack whose layers do not add up to SNEQV: the model's own water-budget check (ERROR) stops both
+    cfg = _cfg("C3", 12, 8)
+    cfg.snow_frac = 1.0
+    xp, st, state = make_case(cfg, tables_usgs)
+    j, i = np.argwhere((state["isnowxy"] == -3) & (st["xland"] < 1.5) & (st["ivgtyp"] != S.ISICE))[0]
+    state["snow"][j, i] += 5.0
+    other = clone_state(state)
+    arr, sc = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), state, 1)
+    status, _ = O.noahmplsm(arr, sc, tables_usgs_struct, nthreads=1)
+    assert status.code != 0 and (status.i, status.j) == (i + 1, j + 1)
+    arr2, sc2 = S.args_from(cfg, st, S.forcing(xp, cfg, 1, st), other, 1)
+    with pytest.raises(RuntimeError, match="Water budget problem"):
+        R.noahmplsm(arr2, sc2)
 
 
 def _same(x, y):
