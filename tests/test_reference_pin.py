@@ -473,7 +473,7 @@ def test_snow_routines_on_random_packs(O, R):
     layers with thin, nearly empty, very thick and melting layers -- the layer bookkeeping branches that a model run
     visits only now and then -- called by name in the translated reference and through the oracle's probes."""
     import ctypes as C
-    L = O.lib()
+    L = C.CDLL(O.build())   # a handle of its own: other tests declare argument types on the shared one
     rng = np.random.default_rng(23)
     f = np.float32
     zsoil = np.array([-0.1, -0.4, -1.0, -2.0], f)
